@@ -1,0 +1,365 @@
+"""ORACLE (test infrastructure, not product code) -- the four ManiSDP primal drivers.
+
+CPU restatement (NumPy/SciPy FP64, dense X / dense eig exactly as the reference does) of
+
+  * src/primal/ManiSDP_onlyunitdiag.m   (closures :117-130, outer loop :38-84, line search :101-115)
+  * src/primal/ManiSDP_unitdiag.m       (closures :152-171, outer loop :51-113, line search :131-150)
+  * src/primal/ManiSDP_unittrace.m      (closures :156-177, outer loop :52-117)
+  * src/primal/ManiSDP.m                (closures :149-165, outer loop :52-113)
+
+driving oracle/manopt_rtr.py in place of Manopt's trustregions.  It is the parity yardstick for the
+CUDA engine and the CPU baseline timed by bench.py; nothing in the product path imports it.
+
+PARITY PIN: the reference ships no expected optima and cannot run here (no
+MATLAB/Octave).  The oracle is pinned by tests/test_oracle_kats.py against independent known
+answers: SDPLIB optimal values listed in data/sdplib/README (maxG11 629.1648, ...), a brute-force
+BQP minimum, DIMACS theta values of Hamming graphs, and the survey's recorded optima
+(BASELINE.md section 2).
+
+LAYOUT: the factor is always (n, p) with one ROW per vertex (see oracle/manopt_rtr.py).  `At` is
+scipy CSC (n*n, m) over the column-major vec of X.
+
+Extensions over the reference (documented, needed for deterministic parity tests):
+  * options['Y0'] accepted by all four drivers (reference: only unittrace / ManiSDP, :36-40);
+  * options['seed'] selects the NumPy generator used where the reference calls randn;
+  * options['stale_eG'] (onlyunitdiag only, default True = reference behaviour): the reference's
+    hess closure reads the shared variable eG that cost() overwrites at a REJECTED proposal
+    (ManiSDP_onlyunitdiag.m:118-119,129).  False keeps eG of the accepted point.
+  * data['hv_count'], data['tr_iters'], data['iters'] counters (the reference has none).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+from .manopt_rtr import Euclid, ObliqueT, Sphere, trustregions
+
+# option defaults, SURVEY.md Appendix B (source lines cited there)
+DEFAULTS = {
+    "onlyunitdiag": dict(p0=2, AL_maxiter=20, tol=1e-8, theta=1e-1, delta=8, alpha=0.5,
+                         tolgradnorm=1e-8, TR_maxinner=100, TR_maxiter=40, line_search=0),
+    "unitdiag": dict(p0=2, AL_maxiter=300, gama=2, sigma0=1e-3, sigma_min=1e-2, sigma_max=1e7,
+                     tol=1e-8, theta=1e-3, delta=8, alpha=0.1, tolgradnorm=1e-8, TR_maxinner=20,
+                     TR_maxiter=4, tau1=1, tau2=1, line_search=0),
+    "unittrace": dict(p0=1, AL_maxiter=1000, gama=2, sigma0=1e1, sigma_min=1e2, sigma_max=1e7,
+                      tol=1e-8, theta=1e-2, delta=8, alpha=0.05, tolgradnorm=1e-8, TR_maxinner=40,
+                      TR_maxiter=3, tau1=1e-5, tau2=1e-4, line_search=1),
+    "general": dict(p0=1, AL_maxiter=1000, gama=2, sigma0=1e-2, sigma_min=1e-1, sigma_max=1e7,
+                    tol=1e-8, theta=1e-2, delta=8, alpha=0.1, tolgradnorm=1e-8, TR_maxinner=20,
+                    TR_maxiter=4, tau1=1e-2, tau2=1e-1, line_search=1),
+}
+
+
+def _opts(kind, options):
+    o = dict(DEFAULTS[kind])
+    o.update(options or {})
+    o.setdefault("seed", 0)
+    o.setdefault("verbose", False)
+    return o
+
+
+def _mat(v, n):
+    """reshape(v, n, n) of a column-major vec."""
+    return np.asarray(v).reshape(n, n, order="F")
+
+
+def _vec(Xm):
+    return np.asarray(Xm).reshape(-1, order="F")
+
+
+# --------------------------------------------------------------------------------------------
+# closures
+# --------------------------------------------------------------------------------------------
+class OnlyUnitDiagProblem:
+    """ManiSDP_onlyunitdiag.m:117-130 (f = 0.5 <C, Y Y'>)."""
+
+    def __init__(self, C, p, stale_eG=True):
+        self.C = sp.csr_matrix(C)
+        self.M = ObliqueT(self.C.shape[0], p)
+        self.stale = stale_eG
+        self.YC = self.eG = None  # state of the last cost() call (the reference's shared variables)
+        self._kept = None
+
+    def cost(self, Y):
+        self._prev = (self.YC, self.eG)
+        self.YC = self.C @ Y  # :118  (C symmetric: (Y_ref*C)' = C*Y)
+        self.eG = np.sum(self.YC * Y, axis=1, keepdims=True)  # :119
+        return 0.5 * float(self.eG.sum())  # :120
+
+    def accept(self, ok):
+        if not ok and not self.stale:
+            self.YC, self.eG = self._prev  # keep the accepted point's eG (correct maths)
+
+    def grad(self, Y):
+        return self.YC - Y * self.eG  # :124
+
+    def hess(self, Y, U):
+        eH = self.C @ U  # :128
+        return eH - Y * np.sum(Y * eH, axis=1, keepdims=True) - U * self.eG  # :129
+
+
+class AffineProblem:
+    """Closures of ManiSDP_unitdiag.m:152-171 (kind 'unitdiag'), ManiSDP_unittrace.m:156-177
+    ('unittrace') and ManiSDP.m:149-165 ('general') on f(Y) = c'x + sigma/2 |A x - b - y/sigma|^2,
+    x = vec(Y Y')."""
+
+    def __init__(self, kind, At, b, c, n, p, y, sigma):
+        self.kind, self.n = kind, n
+        self.At = At
+        self.A = At.T.tocsr()
+        self.b, self.c, self.y, self.sigma = b, c, y, sigma
+        self.M = {"unitdiag": ObliqueT, "unittrace": Sphere, "general": Euclid}[kind](n, p)
+        self.Axb = None
+
+    # cost at an arbitrary point without touching the closure state (the reference's `co`)
+    def co(self, Y):
+        x = _vec(Y @ Y.T)
+        Axb = self.A @ x - self.b - self.y / self.sigma
+        return float(self.c @ x + self.sigma / 2 * (Axb @ Axb))
+
+    def cost(self, Y):
+        x = _vec(Y @ Y.T)
+        self.Axb = self.A @ x - self.b - self.y / self.sigma
+        self._Ycost = Y
+        return float(self.c @ x + 0.5 * self.sigma * (self.Axb @ self.Axb))
+
+    def accept(self, ok):
+        pass  # every closure that reads shared state is only called after an accepted cost()
+
+    def grad(self, Y):
+        n = self.n
+        self.eS = _mat(self.c + self.sigma * (self.At @ self.Axb), n)
+        if self.kind == "unitdiag":  # ManiSDP_unitdiag.m:159-164
+            eG = 2 * (self.eS @ Y)
+            self.YeG = np.sum(Y * eG, axis=1, keepdims=True)
+            return eG - Y * self.YeG
+        if self.kind == "unittrace":  # ManiSDP_unittrace.m:161-164 (built inside cost there)
+            self.z = float(np.sum((self.eS @ Y) * Y))
+            return 2 * (self.eS @ Y) - 2 * self.z * Y
+        return 2 * (self.eS @ Y)  # ManiSDP.m:156-159
+
+    def hess(self, Y, U):
+        n, s = self.n, self.sigma
+        if self.kind == "unitdiag":  # ManiSDP_unitdiag.m:166-171 : YU(i,j) = <Y_i, U_j>
+            YU = Y @ U.T
+        else:  # ManiSDP_unittrace.m:172 / ManiSDP.m:162 : YU = U*Y'
+            YU = U @ Y.T
+        AyU = _mat(self.At @ (self.A @ _vec(YU)), n)
+        H = 2 * (self.eS @ U) + 4 * s * (AyU @ Y)
+        if self.kind == "unitdiag":
+            return H - Y * np.sum(Y * H, axis=1, keepdims=True) - U * self.YeG
+        if self.kind == "unittrace":  # :174-176
+            return H - float(np.vdot(H, Y)) * Y - 2 * self.z * U
+        return H
+
+
+# --------------------------------------------------------------------------------------------
+# shared pieces of the outer loops
+# --------------------------------------------------------------------------------------------
+def _normalize(kind, Y):
+    if kind in ("onlyunitdiag", "unitdiag"):
+        return Y / np.sqrt(np.sum(Y * Y, axis=1, keepdims=True))
+    if kind == "unittrace":
+        return Y / np.linalg.norm(Y)
+    return Y
+
+
+def _line_search(kind, co, Y, U):
+    """ManiSDP_unitdiag.m:138-150 (identical in the other three drivers up to the normalisation)."""
+    alpha = 1.0
+    cost0 = co(Y)
+    i = 1
+    nY = _normalize(kind, Y + alpha * U)
+    while i <= 15 and co(nY) - cost0 > -1e-3:
+        alpha *= 0.8
+        nY = _normalize(kind, Y + alpha * U)
+        i += 1
+    return nY
+
+
+def _rank_cut(Y, theta):
+    """svd(Y) rank estimate and truncation (ManiSDP_unitdiag.m:72-74,93-96 in row layout):
+    returns (r, Y_r) with Y_r = U_r diag(e_r) (n x r)."""
+    Us, e, _ = np.linalg.svd(Y, full_matrices=False)
+    r = int(np.sum(e >= theta * e[0]))
+    return r, Us[:, :r] * e[:r]
+
+
+def _escape(kind, o, Y, vS, nne):
+    """append nne escape directions (ManiSDP_unitdiag.m:97-107 and siblings).  Returns (Y, U)."""
+    n, p = Y.shape
+    V = vS[:, :nne]
+    U = None
+    if o["line_search"] == 1:
+        U = np.hstack([np.zeros((n, p)), V])
+        Y = np.hstack([Y, np.zeros((n, nne))])
+    else:
+        Y = _normalize(kind, np.hstack([Y, o["alpha"] * V]))
+    return Y, U
+
+
+# --------------------------------------------------------------------------------------------
+# drivers
+# --------------------------------------------------------------------------------------------
+def ManiSDP_onlyunitdiag(C, options=None):
+    """[X, obj, data] of src/primal/ManiSDP_onlyunitdiag.m:6."""
+    o = _opts("onlyunitdiag", options)
+    C = sp.csr_matrix(C)
+    n = C.shape[0]
+    rng = np.random.default_rng(o["seed"])
+    p = o["p0"]
+    Y = o.get("Y0")
+    if Y is not None:
+        Y = np.array(Y, dtype=np.float64)
+        p = Y.shape[1]
+    U = None
+    data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[])
+    t0 = time.perf_counter()
+    dinf0 = None
+    Cd = None
+    for it in range(1, o["AL_maxiter"] + 1):
+        data["fac_size"].append(p)
+        prob = OnlyUnitDiagProblem(C, p, o.get("stale_eG", True))
+        if Y is None:
+            Y = prob.M.rand(rng)  # trustregions.m:390-392
+        if U is not None:
+            Y = _line_search("onlyunitdiag", lambda Z: float(np.sum((C @ Z) * Z)), Y, U)  # :101-115
+        res = trustregions(prob, Y, maxiter=o["TR_maxiter"], maxinner=o["TR_maxinner"],
+                           tolgradnorm=o["tolgradnorm"])
+        Y = res.x
+        data["hv_count"] += res.hv_count
+        data["tr_iters"] += len(res.info) - 1
+        gradnorm = res.info[-1].gradnorm
+        X = Y @ Y.T  # :45
+        if Cd is None:
+            Cd = C.toarray()
+        z = np.sum(Cd * X, axis=0)  # :46
+        obj = float(z.sum())
+        S = Cd - np.diag(z)
+        dS, vS = np.linalg.eigh(S)  # :50
+        dinf = max(0.0, -dS[0]) / (1 + dS[-1])
+        r, Yr = _rank_cut(Y, o["theta"])
+        if o["verbose"]:
+            print(f"Iter {it}, obj:{obj:0.8f}, dinf:{dinf:0.1e}, r:{r}, p:{p}, time:{time.perf_counter()-t0:0.2f}s")
+        if dinf < o["tol"]:
+            break
+        if it % 20 == 0:  # :61-69
+            if it > 50 and dinf > dinf0:
+                data["status"] = 2
+                break
+            dinf0 = dinf
+        if r <= p - 1:
+            Y, p = Yr, r
+        nne = max(min(int(np.sum(dS < 0)), o["delta"]), 1)  # :74
+        Y, U = _escape("onlyunitdiag", o, Y, vS, nne)
+        p += nne
+    data.update(X=X, S=S, z=z, dinf=dinf, gradnorm=gradnorm, time=time.perf_counter() - t0, Y=Y,
+                iters=it, obj=obj)
+    if data["status"] == 0 and dinf > o["tol"]:
+        data["status"] = 1
+    return X, obj, data
+
+
+def _affine_driver(kind, At, b, c, K, options):
+    o = _opts(kind, options)
+    n = int(K["s"] if isinstance(K, dict) else K)
+    At = sp.csc_matrix(At)
+    b = np.asarray(b.todense()).ravel() if sp.issparse(b) else np.asarray(b, dtype=np.float64).ravel()
+    c = np.asarray(c.todense()).ravel() if sp.issparse(c) else np.asarray(c, dtype=np.float64).ravel()
+    A = At.T.tocsr()
+    rng = np.random.default_rng(o["seed"])
+    p = o["p0"]
+    sigma = o["sigma0"]
+    gama = o["gama"]
+    y = np.zeros(len(b))
+    normb = 1 + np.linalg.norm(b)
+    Y = o.get("Y0")
+    if Y is not None:
+        Y = np.array(Y, dtype=np.float64)
+        p = Y.shape[1]
+    U = None
+    data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[])
+    check_every, check_after = (50, 100) if kind == "unitdiag" else (20, 50)
+    t0 = time.perf_counter()
+    gap0 = pinf0 = dinf0 = None
+    for it in range(1, o["AL_maxiter"] + 1):
+        data["fac_size"].append(p)
+        prob = AffineProblem(kind, At, b, c, n, p, y, sigma)
+        if Y is None:
+            Y = prob.M.rand(rng)
+        if U is not None:
+            Y = _line_search(kind, prob.co, Y, U)
+        res = trustregions(prob, Y, maxiter=o["TR_maxiter"], maxinner=o["TR_maxinner"],
+                           tolgradnorm=o["tolgradnorm"])
+        Y = res.x
+        data["hv_count"] += res.hv_count
+        data["tr_iters"] += len(res.info) - 1
+        gradnorm = res.info[-1].gradnorm
+        X = Y @ Y.T
+        x = _vec(X)
+        obj = float(c @ x)
+        Axb = A @ x - b
+        pinf = float(np.linalg.norm(Axb)) / normb
+        y = y - sigma * Axb
+        eS = _mat(c - At @ y, n)
+        if kind == "unitdiag":  # ManiSDP_unitdiag.m:65-70
+            z = np.sum(X * eS, axis=0)
+            S = eS - np.diag(z)
+            by = float(b @ y + z.sum())
+        elif kind == "unittrace":  # ManiSDP_unittrace.m:65-70
+            z = float(np.sum(eS * X))
+            S = eS - z * np.eye(n)
+            by = float(b @ y + z)
+        else:  # ManiSDP.m:64-68
+            z = None
+            S = eS
+            by = float(b @ y)
+        dS, vS = np.linalg.eigh(S)
+        dinf = max(0.0, -dS[0]) / (1 + dS[-1])
+        gap = abs(obj - by) / (abs(by) + abs(obj) + 1)
+        r, Yr = _rank_cut(Y, o["theta"])
+        if o["verbose"]:
+            print(f"Iter {it}, obj:{obj:0.8f}, gap:{gap:0.1e}, pinf:{pinf:0.1e}, dinf:{dinf:0.1e}, "
+                  f"gradnorm:{gradnorm:0.1e}, r:{r}, p:{p}, sigma:{sigma:0.3f}, "
+                  f"time:{time.perf_counter()-t0:0.2f}s")
+        eta = max(gap, pinf, dinf)
+        if eta < o["tol"]:
+            break
+        if it % check_every == 0:
+            if it > check_after and gap > gap0 and pinf > pinf0 and dinf > dinf0:
+                data["status"] = 2
+                break
+            gap0, pinf0, dinf0 = gap, pinf, dinf
+        if r <= p - 1:
+            Y, p = Yr, r
+        nneg = int(np.sum(dS < 0))
+        nne = max(min(nneg, o["delta"]), 1) if kind == "unitdiag" else min(nneg, o["delta"])
+        Y, U = _escape(kind, o, Y, vS, nne)
+        p += nne
+        if pinf < o["tau1"] * gradnorm:
+            sigma = max(sigma / gama, o["sigma_min"])
+        elif pinf > o["tau2"] * gradnorm:
+            sigma = min(sigma * gama, o["sigma_max"])
+    data.update(X=X, y=y, S=S, z=z, gap=gap, pinf=pinf, dinf=dinf, gradnorm=gradnorm,
+                time=time.perf_counter() - t0, Y=Y, iters=it, obj=obj, sigma=sigma)
+    if data["status"] == 0 and eta > o["tol"]:
+        data["status"] = 1
+    return X, obj, data
+
+
+def ManiSDP_unitdiag(At, b, c, K, options=None):
+    """[X, obj, data] of src/primal/ManiSDP_unitdiag.m:7."""
+    return _affine_driver("unitdiag", At, b, c, K, options)
+
+
+def ManiSDP_unittrace(At, b, c, K, options=None):
+    """[X, obj, data] of src/primal/ManiSDP_unittrace.m:7."""
+    return _affine_driver("unittrace", At, b, c, K, options)
+
+
+def ManiSDP(At, b, c, K, options=None):
+    """[X, obj, data] of src/primal/ManiSDP.m:6."""
+    return _affine_driver("general", At, b, c, K, options)
