@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- Hessian-vector products/s of the device-resident Riemannian trust-region loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+Workload at any N (BASELINE.json config 5, the one the 1-8 GPU metric is quoted on; it fits one B200): synthetic sparse
+MaxCut, n = 1e6, Erdos-Renyi "G1 profile" (mean degree 48, unit weights, C = -L/4), factor width p = 64, through the
+ONLYUNITDIAG closures.  A STEP is one trust-region iteration of the hot path (`manisdp_tr_solve` with TR_maxiter = 1,
+TR_maxinner = 16: cost+grad at the proposal, up to 16 Hessian products with their tCG vector passes, retraction,
+accept/reject), continuing from the previous step's point.  value = Hessian products of the K timed steps / device
+time (max over ranks).  Inputs (C: 0.59 GB, Y and the tCG workspace: 0.5 GB each) are far larger than the 126 MB L2, so
+no L2 flush is needed between iterations ("l2": "inputs>L2").
+
+N > 1 (torchrun, one rank per GPU): the same instance ROW-SHARDED -- strong scaling -- with an NCCL
+all-gather of the thin factor per product and an all-reduce of the tCG scalar packet.
+
+The JSON line also carries
+  e2e          the same metric through the public C-ABI calls with HOST buffers: set_Y (H2D) + tr_solve + get_Y (D2H)
+  roofline     dominant kernel k_spmm<EPI_HESS> (fused SpMM + tangent projection): algorithmic bytes / CUDA-event time
+  cpu_baseline the oracle port (NumPy/SciPy restatement of the reference) on this box's host cores, bounded sample
+  kkt          wall time to KKT <= 1e-8 on G-set G1 (config 1) through the drop-in ManiSDP_onlyunitdiag
+
+--impl reference times the reference's CPU path (oracle port: the real reference needs MATLAB, absent here) on the same
+workload and metric, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hessian_vector_products_per_s"
+UNIT = "Hv/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def build_workload(args):
+    from manisdp_matlab_b200 import problems as P
+    t0 = time.perf_counter()
+    if args.workload == "er":
+        n, ei, ej, w = P.synthetic_er(args.n, args.degree, seed=0)
+        name = f"synthetic MaxCut n={args.n} Erdos-Renyi mean degree {args.degree} unit weights (G1 profile), p={args.p}"
+    else:
+        side = int(round(args.n ** 0.5))
+        n, ei, ej, w = P.synthetic_torus(side, seed=0)
+        name = f"synthetic MaxCut {side}x{side} torus +-1 weights (G11/G32 profile), p={args.p}"
+    C = P.maxcut_C(n, ei, ej, w)
+    return n, C, name, time.perf_counter() - t0
+
+
+def start_point(n, p, seed=0):
+    rng = np.random.default_rng(seed)
+    Y = rng.standard_normal((n, p))
+    Y /= np.linalg.norm(Y, axis=1, keepdims=True)
+    return Y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_sample(C, n, p, maxinner, repeats=1):
+    """The oracle port on the host cores: trustregions (1 outer iteration, `maxinner` products) on the same workload."""
+    from oracle.manisdp_ref import OnlyUnitDiagProblem
+    from oracle.manopt_rtr import trustregions
+    Ccsr = C.tocsr()
+    Y = start_point(n, p)
+    hv, t = 0, 0.0
+    for _ in range(repeats):
+        prob = OnlyUnitDiagProblem(Ccsr, p, stale_eG=True)
+        t0 = time.perf_counter()
+        res = trustregions(prob, Y, maxiter=1, maxinner=maxinner, tolgradnorm=1e-8)
+        t += time.perf_counter() - t0
+        hv += res.hv_count
+        Y = res.x
+    return hv, t
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n, C, name, _ = build_workload(args)
+    from oracle.manisdp_ref import OnlyUnitDiagProblem
+    from oracle.manopt_rtr import trustregions
+    Ccsr = C.tocsr()
+    Y = start_point(n, args.p)
+    inner = args.ref_inner
+    for _ in range(args.warmup):
+        res = trustregions(OnlyUnitDiagProblem(Ccsr, args.p), Y, maxiter=1, maxinner=inner, tolgradnorm=1e-8)
+        Y = res.x
+    hv = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = trustregions(OnlyUnitDiagProblem(Ccsr, args.p), Y, maxiter=1, maxinner=inner, tolgradnorm=1e-8)
+        Y = res.x
+        hv += res.hv_count
+    dt = time.perf_counter() - t0
+    val = hv / dt
+    try:
+        import threadpoolctl
+        blas_threads = max([d.get("num_threads", 1) for d in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        blas_threads = 1
+    sample = (f"{args.steps} steps x trustregions(maxiter=1, maxinner={inner}) of the oracle port (NumPy/SciPy "
+              f"restatement of trustregions.m/tCG.m + ManiSDP_onlyunitdiag closures; the MATLAB reference cannot run "
+              f"here); SciPy sparse*dense products are single-threaded like MATLAB's")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "n": n, "p": args.p, "nnzC": int(C.nnz)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(),
+                             "blas_threads": blas_threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "hv": hv}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from manisdp_matlab_b200 import Handle, _lib
+
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, C, name, t_gen = build_workload(args)
+    p = args.p
+    nccl_id = None
+    row_begin, row_end = 0, n
+    if world > 1:
+        obj = [_lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        nccl_id = obj[0]
+        rpr = (n + world - 1) // world
+        row_begin, row_end = min(n, rank * rpr), min(n, (rank + 1) * rpr)
+        Cloc = C[:, row_begin:row_end]  # owned columns == owned rows (C symmetric)
+    else:
+        Cloc = C
+    t0 = time.perf_counter()
+    h = Handle("onlyunitdiag", n, C_csc=Cloc, device=local_rank, rank=rank, world=world, row_begin=row_begin,
+               row_end=row_end, nccl_id=nccl_id)
+    t_create = time.perf_counter() - t0
+    Y0 = start_point(n, p)[row_begin:row_end]
+    Y0p = torch.from_numpy(Y0).pin_memory().numpy() if True else Y0
+    out_host = torch.empty((row_end - row_begin, p), dtype=torch.float64).pin_memory().numpy()
+    h.set_Y(Y0p)
+    use_graph = 0 if world > 1 else args.graph
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return h.tr_solve(maxiter=1, maxinner=args.inner, tolgradnorm=1e-12, use_graph=use_graph)
+
+    # ---- device-resident metric -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    l0 = h.stats().launches_total
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    hv, dev_s = 0, 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = step()
+        hv += info.hv_count
+        dev_s += info.seconds  # CUDA events on the engine's stream, around the whole call
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = h.stats().launches_total - l0
+    tt = torch.tensor([dev_s, wall_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s, wall_s = tt.tolist()
+    value = hv / dev_s
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------------------
+    def e2e_step():
+        h.set_Y(Y0p)
+        i = h.tr_solve(maxiter=1, maxinner=args.inner, tolgradnorm=1e-12, use_graph=use_graph)
+        h.lib.manisdp_get_Y(h._h, _lib._pf(out_host), 0)
+        return i.hv_count
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    hv_e = 0
+    ne = max(2, min(args.steps, 5))
+    for _ in range(ne):
+        hv_e += e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = hv_e / te.item()
+
+    # ---- roofline of the dominant kernel (live CUDA-event timing inside the library) -----------------------------
+    st = h.stats()
+    U = np.random.default_rng(1).standard_normal(Y0.shape)
+    h.slot_set(_lib.SLOT_U, U)
+    h.hess_bench(3)
+    ms = h.hess_bench(args.hv_reps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = st.bytes_per_hv / (ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_spmm<GS,VPL,EPI_HESS> (CSR SpMM + oblique tangent projection, fused)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
+                "traffic": args.traffic, "algorithmic_bytes_per_launch": st.bytes_per_hv,
+                "ms_per_launch": ms, "gflops": st.flops_per_hv / (ms * 1e-3) / 1e9,
+                "includes_allgather": world > 1}
+    h.close()
+    if rank != 0:
+        return
+    # ---- CPU baseline (bounded sample) + config-1 time-to-KKT ----------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        chv, ct = cpu_sample(C, n, p, args.cpu_inner)
+        cpu = {"value": chv / ct, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle port: trustregions(maxiter=1, maxinner={args.cpu_inner}) on the same instance "
+                         f"({chv} Hv + 2 cost evaluations in {ct:.1f} s; SciPy sparse*dense is single-threaded)"}
+    kkt = None
+    if world == 1 and not args.no_kkt:
+        kkt = time_to_kkt()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / max(1, args.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "n": n, "p": p, "nnzC": int(C.nnz), "step": f"tr_solve(TR_maxiter=1, "
+                       f"TR_maxinner={args.inner})", "l2": "inputs>L2", "tcg_loop": "cuda-graph WHILE" if use_graph
+                       else "stream", "partition": "rows" if world > 1 else "single"},
+            "hv": hv, "wall_ms_per_step": 1e3 * wall_s / max(1, args.steps),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(Y0.nbytes),
+                    "d2h_bytes_per_step": int(out_host.nbytes) + 256, "steps": ne},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "setup_s": {"generate": t_gen, "create": t_create}, "kkt": kkt}
+    print(json.dumps(line), flush=True)
+
+
+def time_to_kkt():
+    """BASELINE config 1 through the drop-in driver: wall time to dinf <= 1e-8 on G-set G1."""
+    from manisdp_matlab_b200 import ManiSDP_onlyunitdiag, problems as P
+    d = np.load(os.path.join(ROOT, "tests", "golden", "G1.npz"))
+    C = P.maxcut_C(int(d["n"]), d["ei"].astype(np.int64), d["ej"].astype(np.int64), d["w"].astype(np.float64))
+    ManiSDP_onlyunitdiag(C, dict(p0=40, verbose=False))  # warm-up (module load, graph instantiation)
+    t0 = time.perf_counter()
+    X, obj, data = ManiSDP_onlyunitdiag(C, dict(p0=40, verbose=False))
+    dt = time.perf_counter() - t0
+    out = {"instance": "G1 (n=800), ManiSDP_onlyunitdiag p0=40", "seconds": dt, "obj": obj, "dinf": data["dinf"],
+           "hv": int(data["hv_count"]), "tr_seconds": data["tr_seconds"], "status": data["status"]}
+    try:
+        from oracle import manisdp_ref as ref
+        t0 = time.perf_counter()
+        _, obj_c, dc = ref.ManiSDP_onlyunitdiag(C, dict(p0=40, seed=0))
+        out["cpu_port_seconds"] = time.perf_counter() - t0
+        out["cpu_port_obj"] = obj_c
+        out["cpu_port_hv"] = int(dc["hv_count"])
+    except Exception as e:  # the checker is optional here
+        out["cpu_port_error"] = str(e)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="er", choices=["er", "torus"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--p", type=int, default=64)
+    ap.add_argument("--degree", type=int, default=48)
+    ap.add_argument("--inner", type=int, default=16)
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--hv-reps", type=int, default=20)
+    ap.add_argument("--cpu-inner", type=int, default=3)
+    ap.add_argument("--ref-inner", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-kkt", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,209 @@
+// common.cuh -- shared declarations of the B200 ManiSDP engine (internal; the public surface is include/manisdp_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/manisdp_b200.h"
+
+#define MSDP_MAX_BLOCKS 2048   // upper bound on the grid of any reducing kernel (partials buffer rows)
+#define MSDP_NQ 8              // reduction lanes per kernel (distinct scalars reduced in one pass)
+#define MSDP_THREADS 256
+
+enum { MF_OBLIQUE = 0, MF_SPHERE = 1, MF_EUCLID = 2 };
+enum { MODE_NONE = 0, MODE_SPARSE = 1, MODE_DENSE = 2 };
+
+// ---- device-resident scalar state of one trust-region solve ------------------------------------------------------
+// Only the LAST block of a kernel (ticket pattern) writes it, after every block of that kernel has read what it
+// needs, so kernels need no double-buffering of scalars and no host round trip (SURVEY 7 "hard parts": latency).
+struct RtrState {
+  // trust-region level (trustregions.m:441-767)
+  double fx, gradnorm2, Delta, Delta_bar, rho_prime, rho_regularization;
+  double fprop, gradnorm2_prop, rho, rhonum, rhoden, norm_eta;
+  // tCG level (tCG.m:95-292)
+  double z_r, d_Pd, e_Pd, e_Pe, e_Pe_new, model_value, norm_r0, r_r, alpha, beta, tau, d_Hd;
+  double eta_g, eta_Heta;   // <eta, grad>, <eta, Hess eta> of the returned tCG iterate
+  double y_r, y_d;          // sphere only: <Y, r>, <Y, mdelta>
+  double kappa, theta;
+  // per-point scalars of the affine closures: [pt] = value at point buffer pt
+  double zsph[2];           // unittrace: z = <Y, eS Y>   (ManiSDP_unittrace.m:162)
+  double cx[2];             // <C, YY'>
+  double rr[2];             // |A(YY') - b - y/sigma|^2
+  double sigma;
+  double tmp[8];            // scratch scalars between kernels of one closure
+  int pt;                   // which of the two point buffers holds the current (accepted) point
+  int accepted, tr_iter;
+  int stop, j, maxinner, mininner, branch, eta_cur;
+  int hv_count;
+  unsigned int ticket;
+};
+
+struct Csr {  // row lists on the device (int32 indices; n, nnz < 2^31)
+  int *rowptr = nullptr, *col = nullptr;
+  double* val = nullptr;
+  int64_t nrows = 0, nnz = 0;
+};
+
+// constraint pattern of At for the sparse ("SDDMM / scatter-SpMM") path
+struct ASparse {
+  // by constraint k (CSC order of At): entry e in [kptr[k], kptr[k+1]) -> (ei[e], ej[e], ea[e])
+  int *kptr = nullptr, *ei = nullptr, *ej = nullptr;
+  double* ea = nullptr;
+  // by row i: entry e in [rptr[i], rptr[i+1]) -> (rj[e], rk[e], ra[e])
+  int *rptr = nullptr, *rj = nullptr, *rk = nullptr;
+  double* ra = nullptr;
+  int64_t nnz = 0;
+};
+
+// constraint pattern of At for the dense path: A as CSR over k with linear indices into the n x n matrix, and its
+// transpose as CSR over the linear index
+struct ADense {
+  int* kptr = nullptr;      // m+1
+  int* klin = nullptr;      // nnz: lin = j*n + i  (int32 is enough: n <= 46340 on this path)
+  double* ka = nullptr;
+  int* lptr = nullptr;      // n*n+1
+  int* lk = nullptr;        // nnz
+  double* la = nullptr;
+  int64_t nnz = 0;
+};
+
+struct manisdp_handle {
+  int kind = 0, mf = 0, device = 0;
+  int64_t n = 0, nloc = 0, m = 0, p = 0, ld = 0;
+  int64_t row_begin = 0, row_end = 0;
+  int rank = 0, world = 1;
+  int s_mode = MODE_NONE, a_mode = MODE_NONE;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // problem data
+  Csr C;                    // sparse C (row lists of the owned rows; columns are global)
+  double* Cdense = nullptr; // n x n (dense S mode): C itself
+  double* eS = nullptr;     // n x n (dense S mode): C + sigma*At*r at the current point / C - At*y in kkt
+  double* Mbuf = nullptr;   // n x n scratch (dense A mode): Y U' / scatter target
+  ASparse As;
+  ADense Ad;
+  double *b = nullptr, *y = nullptr;   // m
+  double *resid[2] = {nullptr, nullptr}; // m: r = A(YY') - b - y/sigma at point buffer pt
+  double *wU = nullptr, *wtmp = nullptr; // m
+  double sigma = 1.0;
+  double normb = 0.0;
+  // n x ld arrays
+  double* Ybuf[2] = {nullptr, nullptr};
+  double* Gbuf[2] = {nullptr, nullptr};
+  double* eG[2] = {nullptr, nullptr};    // n: oblique row multipliers (eG / YeG) at point buffer pt
+  double* eta[2] = {nullptr, nullptr};
+  double *r = nullptr, *d = nullptr, *Hd = nullptr, *Uslot = nullptr, *Hslot = nullptr;
+  double* gatherbuf = nullptr;           // sharded: n x ld all-gathered direction
+  size_t cap_elems = 0;                  // capacity (elements) of each n x ld array
+  // scalars
+  RtrState* st = nullptr;                // device
+  RtrState* st_host = nullptr;           // pinned
+  double* partials = nullptr;            // MSDP_NQ x MSDP_MAX_BLOCKS
+  int cache_valid = 0;                   // cost caches valid for Ybuf[pt]
+  int grad_valid = 0;
+  int pt = 0;                            // host mirror of st->pt
+  // eig step
+  double* eigvecs = nullptr;             // n x kcap (ROWS layout, ld = kld)
+  double* eigvals_host = nullptr;
+  int eig_k = 0, eig_kld = 0;
+  double* zdiag = nullptr;               // n: z of the last kkt (diag shift of S)
+  double zshift = 0.0;                   // unittrace: S = eS - z*I
+  // log + stats
+  std::vector<manisdp_tr_iter> log;
+  int64_t hv_total = 0, launches = 0;
+  int num_sms = 148;
+  // CUDA graph cache for the tCG loop
+  cudaGraphExec_t tcg_exec = nullptr;
+  cudaGraph_t tcg_graph = nullptr;
+  int64_t tcg_graph_p = -1;
+  int tcg_graph_maxinner = -1;
+  int64_t graph_l_fixed = 0, graph_l_body = 0;  // kernels per graph launch: outside / inside the WHILE body
+  // NCCL
+  void* nccl_comm = nullptr;
+  std::string err;
+};
+
+// ---- error plumbing ---------------------------------------------------------------------------------------------
+int msdp_fail(manisdp_handle* h, int code, const std::string& msg);
+#define CUDA_TRY(h, expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return msdp_fail(h, MANISDP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+#define MSDP_TRY(expr)          \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != MANISDP_OK) return _s; \
+  } while (0)
+#define KERNEL_CHECK(h)                                                                                \
+  do {                                                                                                 \
+    (h)->launches++;                                                                                   \
+    cudaError_t _e = cudaPeekAtLastError();                                                            \
+    if (_e != cudaSuccess)                                                                             \
+      return msdp_fail(h, MANISDP_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e));    \
+  } while (0)
+
+// ---- row-group geometry -----------------------------------------------------------------------------------------
+// A row of ld doubles (ld % 4 == 0) is handled by GS lanes, each holding VPL double2 vectors: vector index
+// v = lane + GS*t.  GS in {2,4,8,16,32}, VPL in {1,2,4,8}  =>  ld <= 512.
+struct RowGeom {
+  int gs, vpl;
+};
+inline RowGeom row_geom(int64_t ld) {
+  int nvec = (int)(ld / 2);
+  RowGeom g{2, 1};
+  while (g.gs < 32 && g.gs < nvec) g.gs *= 2;
+  while (g.gs * g.vpl < nvec) g.vpl *= 2;
+  return g;
+}
+#define MSDP_MAX_LD 512
+
+#define DISPATCH_GEOM(geom, ...)                                            \
+  do {                                                                      \
+    const RowGeom _g = (geom);                                              \
+    if (_g.vpl == 1) {                                                      \
+      switch (_g.gs) {                                                      \
+        case 2: { constexpr int GS = 2, VPL = 1; __VA_ARGS__; } break;      \
+        case 4: { constexpr int GS = 4, VPL = 1; __VA_ARGS__; } break;      \
+        case 8: { constexpr int GS = 8, VPL = 1; __VA_ARGS__; } break;      \
+        case 16: { constexpr int GS = 16, VPL = 1; __VA_ARGS__; } break;    \
+        default: { constexpr int GS = 32, VPL = 1; __VA_ARGS__; } break;    \
+      }                                                                     \
+    } else if (_g.vpl == 2) { constexpr int GS = 32, VPL = 2; __VA_ARGS__; } \
+    else if (_g.vpl == 4) { constexpr int GS = 32, VPL = 4; __VA_ARGS__; }  \
+    else { constexpr int GS = 32, VPL = 8; __VA_ARGS__; }                   \
+  } while (0)
+
+// grid for a row-group kernel over nrows rows
+inline int rows_grid(const manisdp_handle* h, int64_t nrows, int gs, int blocks_per_sm = 8) {
+  int64_t rows_per_block = (MSDP_THREADS / gs);
+  int64_t nb = (nrows + rows_per_block - 1) / rows_per_block;
+  int64_t cap = (int64_t)h->num_sms * blocks_per_sm;
+  if (cap > MSDP_MAX_BLOCKS) cap = MSDP_MAX_BLOCKS;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+// ---- cross-file entry points ------------------------------------------------------------------------------------
+// closures.cu
+// which >= 0: explicit point buffer; -1: proposal (st->pt^1, chosen on the device); -2: current point (st->pt)
+int msdp_costgrad(manisdp_handle* h, int which, int cg_mode);
+// Hout = Hess f(Y)[D]; tail_mode != TAIL_NONE: inside tCG (point chosen on the device, scalars updated)
+int msdp_hess_dir(manisdp_handle* h, const double* D, double* Hout, int tail_mode);
+// cost of an arbitrary n x ld array Z without touching the closure caches (the reference's `co`, line search)
+int msdp_eval_cost_only(manisdp_handle* h, const double* Z, double* f_host);
+void msdp_invalidate_graph(manisdp_handle* h);
+// rtr.cu
+int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_info* info);
+// eig.cu
+int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, manisdp_kkt_info* out);
+int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r, int64_t* pnew);
+int msdp_escape(manisdp_handle* h, int nne, double alpha, int line_search);
+int msdp_line_search(manisdp_handle* h, double* alpha_out);
+void msdp_eig_release(manisdp_handle* h);
+extern "C" int msdp_ensure_costgrad(manisdp_handle* h);  // cost + gradient caches at the current point (one sync)
+// api.cu helpers
+int msdp_resize(manisdp_handle* h, int64_t p);
+int msdp_sync_state(manisdp_handle* h);  // device RtrState -> st_host (synchronises the stream)

@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference's public drivers over the C ABI.
+
+    [X, obj, data] = ManiSDP_onlyunitdiag(C, options)          src/primal/ManiSDP_onlyunitdiag.m:6
+    [X, obj, data] = ManiSDP_unitdiag(At, b, c, K, options)    src/primal/ManiSDP_unitdiag.m:7
+    [X, obj, data] = ManiSDP_unittrace(At, b, c, K, options)   src/primal/ManiSDP_unittrace.m:7
+    [X, obj, data] = ManiSDP(At, b, c, K, options)             src/primal/ManiSDP.m:6
+
+Same names, argument meaning, option fields / defaults, console lines and `data` fields as the
+MATLAB functions; matlab/*.m are the same few lines written against the MEX gateway.  Everything n-sized runs in
+libmanisdp_b200.so on the GPU: the trust-region solve (trustregions + tCG + closures), the KKT residues, the
+eigen step, the rank step and the escape update.  This file only sequences those calls and applies the scalar rules of
+the outer loop (stopping test, sigma rule, slow-progress abort).  It never imports the oracle and has no CPU path.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import _lib
+
+DEFAULTS = {
+    # ManiSDP_onlyunitdiag.m:8-17
+    "onlyunitdiag": dict(p0=2, AL_maxiter=20, tol=1e-8, theta=1e-1, delta=8, alpha=0.5, tolgradnorm=1e-8,
+                         TR_maxinner=100, TR_maxiter=40, line_search=0),
+    # ManiSDP_unitdiag.m:10-26
+    "unitdiag": dict(p0=2, AL_maxiter=300, gama=2, sigma0=1e-3, sigma_min=1e-2, sigma_max=1e7, tol=1e-8, theta=1e-3,
+                     delta=8, alpha=0.1, tolgradnorm=1e-8, TR_maxinner=20, TR_maxiter=4, tau1=1, tau2=1,
+                     line_search=0),
+    # ManiSDP_unittrace.m:10-25
+    "unittrace": dict(p0=1, AL_maxiter=1000, gama=2, sigma0=1e1, sigma_min=1e2, sigma_max=1e7, tol=1e-8, theta=1e-2,
+                      delta=8, alpha=0.05, tolgradnorm=1e-8, TR_maxinner=40, TR_maxiter=3, tau1=1e-5, tau2=1e-4,
+                      line_search=1),
+    # ManiSDP.m:9-25
+    "general": dict(p0=1, AL_maxiter=1000, gama=2, sigma0=1e-2, sigma_min=1e-1, sigma_max=1e7, tol=1e-8, theta=1e-2,
+                    delta=8, alpha=0.1, tolgradnorm=1e-8, TR_maxinner=20, TR_maxiter=4, tau1=1e-2, tau2=1e-1,
+                    line_search=1),
+}
+# largest n for which the dense outputs X = YY' and data.S are formed (the reference always forms them; at
+# n = 1e6 that is 8 TB, so large problems return data['Y'] instead -- documented extension)
+DENSE_OUTPUT_MAX_N = 6000
+
+
+def _opts(kind, options):
+    o = dict(DEFAULTS[kind])
+    o.update(options or {})
+    o.setdefault("seed", 0)
+    o.setdefault("verbose", True)
+    o.setdefault("use_graph", 1)
+    o.setdefault("eig_tol", 0.0)
+    o.setdefault("device", 0)
+    return o
+
+
+def _say(o, msg):
+    if o["verbose"]:
+        print(msg, flush=True)
+
+
+def _init_point(h, o):
+    Y0 = o.get("Y0")
+    if Y0 is not None:
+        h.set_Y(np.asarray(Y0, dtype=np.float64))
+    else:
+        h.rand_Y(int(o["p0"]), int(o["seed"]))  # trustregions.m:390-392 -> M.rand()
+
+
+def ManiSDP_onlyunitdiag(C, options=None):
+    """min <C,X> s.t. diag(X) = 1, X >= 0  (src/primal/ManiSDP_onlyunitdiag.m)."""
+    import scipy.sparse as sp
+
+    o = _opts("onlyunitdiag", options)
+    C = sp.csc_matrix(C)
+    n = C.shape[0]
+    _say(o, "ManiSDP is starting...")
+    _say(o, f"SDP size: n = {n}, m = {n}")
+    data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[], tr_seconds=0.0)
+    t0 = time.perf_counter()
+    with _lib.Handle("onlyunitdiag", n, C_csc=C, device=o["device"]) as h:
+        _init_point(h, o)
+        staged = False
+        dinf0 = None
+        for it in range(1, int(o["AL_maxiter"]) + 1):
+            data["fac_size"].append(h.p)
+            if staged:
+                h.line_search()  # :40-42
+            info = h.tr_solve(o["TR_maxiter"], o["TR_maxinner"], o["tolgradnorm"], o["use_graph"])  # :43
+            data["hv_count"] += info.hv_count
+            data["tr_iters"] += info.iters
+            data["tr_seconds"] += info.seconds
+            gradnorm = info.gradnorm
+            k = h.kkt(int(o["delta"]), o["eig_tol"], 0)  # :45-51
+            obj, dinf = k.obj, k.dinf
+            p = h.p
+            r, _ = h.rank_cut(o["theta"], apply=False)  # :52-54
+            _say(o, f"Iter {it}, obj:{obj:0.8f}, dinf:{dinf:0.1e}, r:{r}, p:{p}, time:{time.perf_counter()-t0:0.2f}s")
+            if dinf < o["tol"]:
+                _say(o, "Optimality is reached!")
+                break
+            if it % 20 == 0:  # :61-69
+                if it > 50 and dinf > dinf0:
+                    data["status"] = 2
+                    _say(o, "Slow progress!")
+                    break
+                dinf0 = dinf
+            if it == int(o["AL_maxiter"]):
+                break  # the reference still updates Y here, but nothing consumes it afterwards
+            if r <= p - 1:
+                h.rank_cut(o["theta"], apply=True)  # :70-73
+            nne = max(min(k.nneg, int(o["delta"])), 1)  # :74
+            staged = int(o["line_search"]) == 1
+            h.escape(nne, o["alpha"], int(o["line_search"]))  # :75-84
+        Y = h.get_Y()
+        st = h.stats()
+        data["launches"] = st.launches_total
+    z = None
+    X = S = None
+    if n <= DENSE_OUTPUT_MAX_N:
+        X = Y @ Y.T
+        z = np.asarray(C.multiply(X).sum(axis=0)).ravel()
+        S = C.toarray() - np.diag(z)
+    data.update(X=X, S=S, z=z, dinf=dinf, gradnorm=gradnorm, time=time.perf_counter() - t0, Y=Y, iters=it, obj=obj,
+                lam_min=k.lam_min, lam_max=k.lam_max, eig_iters=k.eig_iters, eig_resid=k.eig_resid)
+    if data["status"] == 0 and dinf > o["tol"]:
+        data["status"] = 1
+        _say(o, "Iteration maximum is reached!")
+    _say(o, f"ManiSDP: optimum = {obj:0.8f}, time = {data['time']:0.2f}s")
+    return X, obj, data
+
+
+def _affine_driver(kind, At, b, c, K, options):
+    import scipy.sparse as sp
+
+    o = _opts(kind, options)
+    n = int(K["s"] if isinstance(K, dict) else K)
+    At = sp.csc_matrix(At)
+    bd = np.asarray(b.todense()).ravel() if sp.issparse(b) else np.asarray(b, dtype=np.float64).ravel()
+    m = At.shape[1]
+    _say(o, "ManiSDP is starting...")
+    _say(o, f"SDP size: n = {n}, m = {m}")
+    sigma = float(o["sigma0"])
+    gama = float(o["gama"])
+    data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[], tr_seconds=0.0)
+    check_every, check_after = (50, 100) if kind == "unitdiag" else (20, 50)
+    t0 = time.perf_counter()
+    gap0 = pinf0 = dinf0 = None
+    with _lib.Handle(kind, n, At=At, b=bd, c=c, device=o["device"], force_mode=int(o.get("force_mode", 0))) as h:
+        h.set_dual(np.zeros(m), sigma)
+        _init_point(h, o)
+        staged = False
+        for it in range(1, int(o["AL_maxiter"]) + 1):
+            data["fac_size"].append(h.p)
+            if staged:
+                h.line_search()
+            info = h.tr_solve(o["TR_maxiter"], o["TR_maxinner"], o["tolgradnorm"], o["use_graph"])
+            data["hv_count"] += info.hv_count
+            data["tr_iters"] += info.iters
+            data["tr_seconds"] += info.seconds
+            gradnorm = info.gradnorm
+            k = h.kkt(int(o["delta"]), o["eig_tol"], 1)  # residues, y <- y - sigma*Axb, eig(S)
+            obj, gap, pinf, dinf = k.obj, k.gap, k.pinf, k.dinf
+            p = h.p
+            r, _ = h.rank_cut(o["theta"], apply=False)
+            _say(o, f"Iter {it}, obj:{obj:0.8f}, gap:{gap:0.1e}, pinf:{pinf:0.1e}, dinf:{dinf:0.1e}, "
+                    f"gradnorm:{gradnorm:0.1e}, r:{r}, p:{p}, sigma:{sigma:0.3f}, time:{time.perf_counter()-t0:0.2f}s")
+            eta = max(gap, pinf, dinf)
+            if eta < o["tol"]:
+                _say(o, "Optimality is reached!")
+                break
+            if it % check_every == 0:
+                if it > check_after and gap > gap0 and pinf > pinf0 and dinf > dinf0:
+                    data["status"] = 2
+                    _say(o, "Slow progress!")
+                    break
+                gap0, pinf0, dinf0 = gap, pinf, dinf
+            if it == int(o["AL_maxiter"]):
+                break
+            if r <= p - 1:
+                h.rank_cut(o["theta"], apply=True)
+            nne = min(k.nneg, int(o["delta"]))
+            if kind == "unitdiag":
+                nne = max(nne, 1)  # ManiSDP_unitdiag.m:97 (the other two have no lower bound)
+            staged = int(o["line_search"]) == 1
+            h.escape(nne, o["alpha"], int(o["line_search"]))
+            if pinf < o["tau1"] * gradnorm:  # ManiSDP_unitdiag.m:108-112
+                sigma = max(sigma / gama, o["sigma_min"])
+            elif pinf > o["tau2"] * gradnorm:
+                sigma = min(sigma * gama, o["sigma_max"])
+            h.set_sigma(sigma)
+        Y = h.get_Y()
+        y, _ = h.get_dual()
+        st = h.stats()
+        data["launches"] = st.launches_total
+        data["s_mode"], data["a_mode"] = st.s_mode, st.a_mode
+    X = S = z = None
+    if n <= DENSE_OUTPUT_MAX_N:
+        X = Y @ Y.T
+        cd = np.asarray(c.todense()).ravel() if sp.issparse(c) else np.asarray(c, dtype=np.float64).ravel()
+        eS = (cd - At @ y).reshape(n, n, order="F")
+        if kind == "unitdiag":
+            z = np.sum(X * eS, axis=0)
+            S = eS - np.diag(z)
+        elif kind == "unittrace":
+            z = float(np.sum(X * eS))
+            S = eS - z * np.eye(n)
+        else:
+            S = eS
+    data.update(X=X, y=y, S=S, z=z, gap=gap, pinf=pinf, dinf=dinf, gradnorm=gradnorm, time=time.perf_counter() - t0,
+                Y=Y, iters=it, obj=obj, sigma=sigma, lam_min=k.lam_min, lam_max=k.lam_max, eig_iters=k.eig_iters)
+    if data["status"] == 0 and eta > o["tol"]:
+        data["status"] = 1
+        _say(o, "Iteration maximum is reached!")
+    _say(o, f"ManiSDP: optimum = {obj:0.8f}, time = {data['time']:0.2f}s")
+    return X, obj, data
+
+
+def ManiSDP_unitdiag(At, b, c, K, options=None):
+    """src/primal/ManiSDP_unitdiag.m:7"""
+    return _affine_driver("unitdiag", At, b, c, K, options)
+
+
+def ManiSDP_unittrace(At, b, c, K, options=None):
+    """src/primal/ManiSDP_unittrace.m:7"""
+    return _affine_driver("unittrace", At, b, c, K, options)
+
+
+def ManiSDP(At, b, c, K, options=None):
+    """src/primal/ManiSDP.m:6"""
+    return _affine_driver("general", At, b, c, K, options)
