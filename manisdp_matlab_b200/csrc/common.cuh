@@ -61,10 +61,13 @@ struct ADense {
   int* kptr = nullptr;      // m+1
   int* klin = nullptr;      // nnz: lin = j*n + i  (int32 is enough: n <= 46340 on this path)
   double* ka = nullptr;
-  int* lptr = nullptr;      // n*n+1
+  // transpose restricted to the TOUCHED positions of the n x n matrix (dense S mode, either A mode):
+  // position u -> linear index upos[u], entries [lptr[u], lptr[u+1]) -> (constraint lk[e], value la[e])
+  int* upos = nullptr;      // nu
+  int* lptr = nullptr;      // nu+1
   int* lk = nullptr;        // nnz
   double* la = nullptr;
-  int64_t nnz = 0;
+  int64_t nnz = 0, nu = 0;
 };
 
 struct manisdp_handle {
@@ -79,12 +82,14 @@ struct manisdp_handle {
   Csr C;                    // sparse C (row lists of the owned rows; columns are global)
   double* Cdense = nullptr; // n x n (dense S mode): C itself
   double* eS = nullptr;     // n x n (dense S mode): C + sigma*At*r at the current point / C - At*y in kkt
-  double* Mbuf = nullptr;   // n x n scratch (dense A mode): Y U' / scatter target
+  double* Mbuf = nullptr;   // n x n scratch (dense A mode): Y U'
+  double* Tbuf = nullptr;   // n x n (dense A mode): mat(At * w); untouched positions stay zero
   ASparse As;
   ADense Ad;
   double *b = nullptr, *y = nullptr;   // m
   double *resid[2] = {nullptr, nullptr}; // m: r = A(YY') - b - y/sigma at point buffer pt
   double *wU = nullptr, *wtmp = nullptr; // m
+  double* y_kkt = nullptr;               // y used by the last kkt call (h->y, or h->wtmp when the dual was not updated)
   double sigma = 1.0;
   double normb = 0.0;
   // n x ld arrays
@@ -113,10 +118,11 @@ struct manisdp_handle {
   int64_t hv_total = 0, launches = 0;
   int num_sms = 148;
   // CUDA graph cache for the tCG loop
-  cudaGraphExec_t tcg_exec = nullptr;
-  cudaGraph_t tcg_graph = nullptr;
+  cudaGraphExec_t tcg_exec[2] = {nullptr, nullptr};  // one per value of pt (which buffer is the current point)
+  cudaGraph_t tcg_graph[2] = {nullptr, nullptr};
   int64_t tcg_graph_p = -1;
   int tcg_graph_maxinner = -1;
+  double graph_sigma = -1.0;
   int64_t graph_l_fixed = 0, graph_l_body = 0;  // kernels per graph launch: outside / inside the WHILE body
   // NCCL
   void* nccl_comm = nullptr;

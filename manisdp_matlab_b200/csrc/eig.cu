@@ -749,7 +749,7 @@ int msdp_line_search(manisdp_handle* h, double* alpha_out) {
     k_scaled_copy<<<nb, 256, 0, h->stream>>>(h->Uslot, alpha, h->eta[0], nvec);
     KERNEL_CHECK(h);
     MSDP_TRY(msdp_launch_retract(h, h->Ybuf[h->pt], h->eta[0], h->Ybuf[h->pt ^ 1], 0));  // nY = normalise(Y + alpha*U)
-    MSDP_TRY(msdp_costgrad(h, h->pt ^ 1, CG_PLAIN));
+    MSDP_TRY(msdp_costgrad(h, h->pt ^ 1, CG_COSTONLY));
     const int keep_pt = h->pt;
     MSDP_TRY(msdp_sync_state(h));
     h->pt = keep_pt;

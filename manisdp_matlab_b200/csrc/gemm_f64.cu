@@ -24,11 +24,12 @@ struct GemmArgs {
   int64_t sam, sak, sbk, sbn, ldc;
   int M, N, K;
   double alpha, beta;
-  const int* pred;  // optional device flag: skip the whole kernel when *pred == 0
+  const int* pred;  // optional device flag
+  int pred_sense;   // 0: skip when *pred == 0 ; 1: skip when *pred != 0
 };
 
 __global__ void __launch_bounds__(256) k_gemm_f64(GemmArgs g) {
-  if (g.pred && *g.pred == 0) return;
+  if (g.pred && ((*g.pred == 0) != (g.pred_sense != 0))) return;
   __shared__ double As[BM][BK + PAD];
   __shared__ double Bs[BK][BN + PAD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -111,14 +112,14 @@ static int launch(manisdp_handle* h, const GemmArgs& g) {
 
 // out(n x w, ld = ldo) = alpha * S(n x n, row stride n) * V(n x w, ld = ldv) + beta * out
 int msdp_gemm_nn(manisdp_handle* h, const double* S, int n, const double* V, int ldv, int w, double* out, int ldo,
-                 double alpha, double beta, const int* pred) {
-  GemmArgs g{S, V, out, n, 1, ldv, 1, ldo, n, w, n, alpha, beta, pred};
+                 double alpha, double beta, const int* pred, int pred_sense) {
+  GemmArgs g{S, V, out, n, 1, ldv, 1, ldo, n, w, n, alpha, beta, pred, pred_sense};
   return launch(h, g);
 }
 
 // M(n x n, row stride n) = alpha * P(n x w) * Q(n x w)'
 int msdp_gemm_nt(manisdp_handle* h, const double* P, int ldp, const double* Q, int ldq, int n, int w, double* M,
-                 double alpha, const int* pred) {
-  GemmArgs g{P, Q, M, ldp, 1, 1, ldq, n, n, n, w, alpha, 0.0, pred};
+                 double alpha, const int* pred, int pred_sense) {
+  GemmArgs g{P, Q, M, ldp, 1, 1, ldq, n, n, n, w, alpha, 0.0, pred, pred_sense};
   return launch(h, g);
 }

@@ -26,7 +26,8 @@ enum {
   CG_PLAIN = 0,   // cost + gradient at Ybuf[which]: fill caches, st->tmp[0] = f, st->tmp[1] = |grad|^2
   CG_INIT = 1,    // as PLAIN and also st->fx, st->gradnorm2 (trustregions.m:405)
   CG_TR = 2,      // proposal inside the TR loop: st->fprop, st->gradnorm2_prop, then tr_decide
-  CG_TR_DEFER = 3 // row-sharded variant of CG_TR: local sums in st->tmp[0..1]
+  CG_TR_DEFER = 3, // row-sharded variant of CG_TR: local sums in st->tmp[0..1]
+  CG_COSTONLY = 4  // cost only (line search): st->tmp[0] = f, no cache / gradient side effects for the affine kinds
 };
 
 // spmm.cu (ONLYUNITDIAG closures, ManiSDP_onlyunitdiag.m:117-130)

@@ -75,21 +75,25 @@ static int tr_tail(manisdp_handle* h) {
 }
 
 static void destroy_graph(manisdp_handle* h) {
-  if (h->tcg_exec) cudaGraphExecDestroy(h->tcg_exec);
-  if (h->tcg_graph) cudaGraphDestroy(h->tcg_graph);
-  h->tcg_exec = nullptr;
-  h->tcg_graph = nullptr;
+  for (int i = 0; i < 2; ++i) {
+    if (h->tcg_exec[i]) cudaGraphExecDestroy(h->tcg_exec[i]);
+    if (h->tcg_graph[i]) cudaGraphDestroy(h->tcg_graph[i]);
+    h->tcg_exec[i] = nullptr;
+    h->tcg_graph[i] = nullptr;
+  }
   h->tcg_graph_p = -1;
 }
 void msdp_invalidate_graph(manisdp_handle* h) { destroy_graph(h); }
 
 // Build   tcg_init -> WHILE(cond){ Hv ; update ; direction } -> retract -> cost+grad+accept   as one graph.
+// The affine closures resolve their point buffers on the host, so one graph is built per value of pt (which of the two
+// point buffers is current); the MaxCut kernels select on the device and would work with either.
 static int build_tr_graph(manisdp_handle* h) {
-  destroy_graph(h);
+  const int gi = h->pt;
   const int64_t launches0 = h->launches;
   cudaGraph_t g = nullptr;
   CUDA_TRY(h, cudaGraphCreate(&g, 0));
-  h->tcg_graph = g;
+  h->tcg_graph[gi] = g;
   cudaStream_t s = h->stream;
   // segment A
   CUDA_TRY(h, cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
@@ -133,7 +137,7 @@ static int build_tr_graph(manisdp_handle* h) {
   e2 = cudaStreamEndCapture(s, &dummy);
   if (rc != MANISDP_OK) return rc;
   CUDA_TRY(h, e2);
-  CUDA_TRY(h, cudaGraphInstantiate(&h->tcg_exec, g, 0));
+  CUDA_TRY(h, cudaGraphInstantiate(&h->tcg_exec[gi], g, 0));
   h->tcg_graph_p = h->p;
   h->launches = launches0;  // capture-time launches are not executions
   return MANISDP_OK;
@@ -198,9 +202,11 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
   rec.accepted = 1;
   h->log.push_back(rec);
 
-  if (use_graph && (h->tcg_exec == nullptr || h->tcg_graph_p != h->p || h->tcg_graph_maxinner != opt.maxinner)) {
-    MSDP_TRY(build_tr_graph(h));
+  if (use_graph && (h->tcg_graph_p != h->p || h->tcg_graph_maxinner != opt.maxinner || h->graph_sigma != h->sigma)) {
+    destroy_graph(h);  // kernel arguments (widths, sigma) are baked into the captured launches
+    h->tcg_graph_p = h->p;
     h->tcg_graph_maxinner = opt.maxinner;
+    h->graph_sigma = h->sigma;
   }
   // kernels per tCG iteration / per TR iteration (for the launch counter in graph mode)
   int k = 0, naccepted = 0, stop_reason = 1;
@@ -215,7 +221,8 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
       break;
     }
     if (use_graph) {
-      CUDA_TRY(h, cudaGraphLaunch(h->tcg_exec, h->stream));
+      if (!h->tcg_exec[h->pt]) MSDP_TRY(build_tr_graph(h));
+      CUDA_TRY(h, cudaGraphLaunch(h->tcg_exec[h->pt], h->stream));
     } else {
       MSDP_TRY(msdp_launch_tcg_init(h));
       int done = 0, issued = 0;
