@@ -1,0 +1,90 @@
+"""Time-to-KKT of BASELINE.json configs 1-4 through the drop-in drivers (measurement script, not product code: the
+SeDuMi inputs are built with the oracle's restatement of the reference's generators bqpmom / qsmom / generate_hamming).
+
+    python tools/run_configs.py [g1 g11 g32 bqp20 bqp60 qs20 qs40s theta98 theta102] [--cpu]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+import manisdp_matlab_b200 as M  # noqa: E402
+from manisdp_matlab_b200 import problems as P  # noqa: E402
+from oracle import generators as g  # noqa: E402
+from oracle import manisdp_ref as ref  # noqa: E402
+
+
+def dense_b(b):
+    return np.asarray(b.todense()).ravel() if hasattr(b, "todense") else np.asarray(b).ravel()
+
+
+def run(name, cpu):
+    t0 = time.perf_counter()
+    if name in ("g1", "g11", "g32"):
+        d = np.load(os.path.join(GOLDEN, f"{name.upper()}.npz"))
+        C = P.maxcut_C(int(d["n"]), d["ei"].astype(np.int64), d["ej"].astype(np.int64), d["w"].astype(np.float64))
+        opts = dict(p0=40)
+        call = lambda mod, o: mod.ManiSDP_onlyunitdiag(C, o)
+        n, m = C.shape[0], C.shape[0]
+    elif name.startswith("bqp"):
+        q = int(name[3:])
+        d = np.load(os.path.join(GOLDEN, f"bqp_{q}_1.npz"))
+        At, b, c, K = g.bqpmom(q, d["Q"], d["e"])
+        c = c / np.abs(c).max()
+        b = dense_b(b)
+        opts = dict(tol=1e-8)
+        call = lambda mod, o: mod.ManiSDP_unitdiag(At, b, c, K, o)
+        n, m = int(K["s"]), At.shape[1]
+    elif name.startswith("qs"):
+        q = int(name[2:4])
+        if name.endswith("s"):  # synthetic coefficients (qs_c_60 is missing from the reference tree)
+            from math import comb
+            coe = np.random.default_rng(q).standard_normal(comb(q + 4, 4) if False else g.qs_num_coe(q))
+        else:
+            coe = np.load(os.path.join(GOLDEN, f"qs_c_{q}_1.npz"))["coe"]
+        At, b, c, K = g.qsmom(q, coe)
+        b = dense_b(b)
+        opts = dict(tol=1e-8, theta=1e-2, tau1=0.02)
+        call = lambda mod, o: mod.ManiSDP(At, b, c, K, o)
+        n, m = int(K["s"]), At.shape[1]
+    elif name.startswith("theta"):
+        k, dd = {"theta756": (7, [5, 6]), "theta98": (9, 8), "theta102": (10, 2), "theta112": (11, 2)}[name]
+        At, b, c, K = g.generate_hamming(k, dd)
+        b = dense_b(b)
+        opts = dict(tol=1e-8, sigma0=1e5, sigma_max=1e8, line_search=1, TR_maxiter=10, TR_maxinner=100)
+        call = lambda mod, o: mod.ManiSDP_unittrace(At, b, c, K, o)
+        n, m = int(K["s"]), At.shape[1]
+    else:
+        raise SystemExit(f"unknown config {name}")
+    t_gen = time.perf_counter() - t0
+    o = dict(opts, verbose=False)
+    t0 = time.perf_counter()
+    X, obj, data = call(M, o)
+    dt = time.perf_counter() - t0
+    eta = max(data.get("gap", 0.0), data.get("pinf", 0.0), data["dinf"])
+    rec = dict(config=name, n=n, m=m, seconds=dt, obj=obj, eta=eta, iters=data["iters"], hv=int(data["hv_count"]),
+               tr_seconds=data["tr_seconds"], hv_per_s=data["hv_count"] / max(data["tr_seconds"], 1e-9),
+               status=data["status"], launches=int(data.get("launches", 0)), gen_seconds=t_gen,
+               modes=[data.get("s_mode"), data.get("a_mode")], p_max=max(data["fac_size"]))
+    if cpu:
+        t0 = time.perf_counter()
+        Xc, objc, dc = call(ref, dict(opts, seed=0))
+        rec.update(cpu_seconds=time.perf_counter() - t0, cpu_obj=objc, cpu_hv=int(dc["hv_count"]),
+                   cpu_iters=dc["iters"], cpu_eta=max(dc.get("gap", 0.0), dc.get("pinf", 0.0), dc["dinf"]),
+                   cpu_cores=os.cpu_count())
+    print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["g1", "g11", "bqp20", "theta756"]
+    for nm in names:
+        try:
+            run(nm, "--cpu" in sys.argv)
+        except Exception as e:  # keep going: one failing config must not hide the others
+            print(json.dumps(dict(config=nm, error=repr(e))), flush=True)
