@@ -1,0 +1,236 @@
+/*
+ * manisdp_mex.cpp -- thin MATLAB MEX gateway over the C ABI of libmanisdp_b200.so (include/manisdp_b200.h).
+ *
+ *   mex -R2017b -I../include manisdp_mex.cpp -L../manisdp_matlab_b200 -lmanisdp_b200
+ *
+ * (separate-complex API, so mxGetPr / mxGetIr / mxGetJc hand out the CSC arrays without a copy; mwIndex is uint64 on
+ * every 64-bit MATLAB, which is exactly the index type the C ABI takes.)  The build container has no mex.h, so this
+ * file is source-only there; tests/ drive the same C ABI through ctypes (manisdp_matlab_b200/_lib.py).
+ *
+ * Usage from MATLAB (see ManiSDP_onlyunitdiag.m etc. in this directory):
+ *   h    = manisdp_mex('create', kind, n, C)                      kind 0: C sparse n x n
+ *   h    = manisdp_mex('create', kind, n, At, b, c)               kind 1..3: SeDuMi data
+ *          manisdp_mex('set_Y', h, Y, layout)                     layout 0: p x n (unit-diag drivers), 1: n x p
+ *   Y    = manisdp_mex('get_Y', h, layout)
+ *          manisdp_mex('rand_Y', h, p, seed)
+ *          manisdp_mex('set_dual', h, y, sigma) / manisdp_mex('set_sigma', h, sigma)
+ *   [y, sigma] = manisdp_mex('get_dual', h)
+ *   info = manisdp_mex('tr_solve', h, opts)                       opts fields: maxiter, maxinner, tolgradnorm, use_graph
+ *   k    = manisdp_mex('kkt', h, delta, eig_tol, update_dual)
+ *   [r, p] = manisdp_mex('rank_cut', h, theta, apply)
+ *          manisdp_mex('escape', h, nne, alpha, line_search)
+ *   a    = manisdp_mex('line_search', h)
+ *   [vals, vecs] = manisdp_mex('get_eigs', h, k)
+ *   f = manisdp_mex('cost', h); [G, gn] = manisdp_mex('grad', h); H = manisdp_mex('hess', h, U)   (A/B debugging)
+ *          manisdp_mex('destroy', h)
+ *
+ * Ownership: prhs[] stay MATLAB's (read-only, copied to the device by the library); plhs[] are created here with
+ * mxCreate* and handed to MATLAB (same convention as the reference's src/C-files/lincombc.cpp:16,30,39).  Errors are
+ * raised with mexErrMsgIdAndTxt("ManiSDP:b200:<code>", msg) (reference convention: src/C-files/innerc.cpp:5-10).
+ */
+#include <string.h>
+#include <string>
+#include <vector>
+#include "manisdp_b200.h"
+#include "mex.h"
+
+static std::vector<manisdp_t*> g_handles;
+
+static void at_exit() {
+  for (manisdp_t* h : g_handles)
+    if (h) manisdp_destroy(h);
+  g_handles.clear();
+}
+
+static void fail(manisdp_t* h, int rc, const char* what) {
+  const char* msg = manisdp_last_error(h);
+  char id[64];
+  snprintf(id, sizeof(id), "ManiSDP:b200:E%d", -rc);
+  mexErrMsgIdAndTxt(id, "%s failed (%d): %s", what, rc, msg ? msg : "");
+}
+#define CK(h, expr, what)        \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) fail(h, _rc, what); \
+  } while (0)
+
+static manisdp_t* handle_of(const mxArray* a) {
+  if (!mxIsUint64(a) || mxGetNumberOfElements(a) != 1) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "bad handle");
+  const uint64_t idx = *(const uint64_t*)mxGetData(a);
+  if (idx >= g_handles.size() || !g_handles[idx]) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "stale handle");
+  return g_handles[idx];
+}
+
+static double field_or(const mxArray* s, const char* name, double dflt) {
+  const mxArray* f = mxIsStruct(s) ? mxGetField(s, 0, name) : nullptr;
+  return f ? mxGetScalar(f) : dflt;
+}
+
+static mxArray* scalar_struct(const char** names, const double* vals, int nf) {
+  mxArray* s = mxCreateStructMatrix(1, 1, nf, names);
+  for (int i = 0; i < nf; ++i) mxSetFieldByNumber(s, 0, i, mxCreateDoubleScalar(vals[i]));
+  return s;
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "first argument must be a command string");
+  char cmd[32];
+  mxGetString(prhs[0], cmd, sizeof(cmd));
+  const std::string c(cmd);
+
+  if (c == "create") {
+    manisdp_problem pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.kind = (int32_t)mxGetScalar(prhs[1]);
+    pb.n = (int64_t)mxGetScalar(prhs[2]);
+    pb.world = 1;
+    pb.row_end = pb.n;
+    std::vector<double> bdense;
+    if (pb.kind == MANISDP_ONLYUNITDIAG) {
+      const mxArray* C = prhs[3];
+      if (!mxIsSparse(C) || !mxIsDouble(C)) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "C must be sparse double");
+      pb.C_jc = (const uint64_t*)mxGetJc(C);
+      pb.C_ir = (const uint64_t*)mxGetIr(C);
+      pb.C_pr = mxGetPr(C);
+    } else {
+      const mxArray *At = prhs[3], *b = prhs[4], *cc = prhs[5];
+      if (!mxIsSparse(At)) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "At must be sparse (SeDuMi format)");
+      pb.m = (int64_t)mxGetN(At);
+      pb.At_jc = (const uint64_t*)mxGetJc(At);
+      pb.At_ir = (const uint64_t*)mxGetIr(At);
+      pb.At_pr = mxGetPr(At);
+      if (mxIsSparse(b)) {  // bqpmom.m:37 builds a sparse b
+        bdense.assign((size_t)pb.m, 0.0);
+        const mwIndex *jc = mxGetJc(b), *ir = mxGetIr(b);
+        const double* pr = mxGetPr(b);
+        for (mwIndex e = jc[0]; e < jc[mxGetN(b)]; ++e) bdense[ir[e]] = pr[e];
+        pb.b = bdense.data();
+      } else {
+        pb.b = mxGetPr(b);
+      }
+      if (mxIsSparse(cc)) {
+        pb.c_ir = (const uint64_t*)mxGetIr(cc);
+        pb.c_pr = mxGetPr(cc);
+        pb.c_nnz = (int64_t)mxGetJc(cc)[1];
+      } else {
+        pb.c_pr = mxGetPr(cc);
+        pb.c_nnz = (int64_t)mxGetNumberOfElements(cc);
+      }
+    }
+    manisdp_t* h = nullptr;
+    int rc = manisdp_create(&h, &pb);
+    if (rc != 0) fail(nullptr, rc, "manisdp_create");
+    if (g_handles.empty()) {
+      mexLock();
+      mexAtExit(at_exit);
+    }
+    g_handles.push_back(h);
+    plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+    *(uint64_t*)mxGetData(plhs[0]) = (uint64_t)(g_handles.size() - 1);
+    return;
+  }
+
+  manisdp_t* h = handle_of(prhs[1]);
+  manisdp_stats st;
+
+  if (c == "destroy") {
+    const uint64_t idx = *(const uint64_t*)mxGetData(prhs[1]);
+    manisdp_destroy(h);
+    g_handles[idx] = nullptr;
+  } else if (c == "set_Y") {
+    const int layout = (int)mxGetScalar(prhs[3]);
+    const int64_t p = layout == MANISDP_LAYOUT_ROWS ? (int64_t)mxGetM(prhs[2]) : (int64_t)mxGetN(prhs[2]);
+    CK(h, manisdp_set_Y(h, mxGetPr(prhs[2]), p, layout), "set_Y");
+  } else if (c == "get_Y") {
+    const int layout = (int)mxGetScalar(prhs[2]);
+    CK(h, manisdp_get_stats(h, &st), "get_stats");
+    plhs[0] = layout == MANISDP_LAYOUT_ROWS ? mxCreateDoubleMatrix((mwSize)st.p, (mwSize)st.n, mxREAL)
+                                            : mxCreateDoubleMatrix((mwSize)st.n, (mwSize)st.p, mxREAL);
+    CK(h, manisdp_get_Y(h, mxGetPr(plhs[0]), layout), "get_Y");
+  } else if (c == "rand_Y") {
+    CK(h, manisdp_rand_Y(h, (int64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])), "rand_Y");
+  } else if (c == "set_dual") {
+    CK(h, manisdp_set_dual(h, mxGetPr(prhs[2]), mxGetScalar(prhs[3])), "set_dual");
+  } else if (c == "set_sigma") {
+    CK(h, manisdp_set_sigma(h, mxGetScalar(prhs[2])), "set_sigma");
+  } else if (c == "get_dual") {
+    CK(h, manisdp_get_stats(h, &st), "get_stats");
+    plhs[0] = mxCreateDoubleMatrix((mwSize)st.m, 1, mxREAL);
+    double sigma = 0;
+    CK(h, manisdp_get_dual(h, mxGetPr(plhs[0]), &sigma), "get_dual");
+    if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(sigma);
+  } else if (c == "tr_solve") {
+    manisdp_tr_options o;
+    memset(&o, 0, sizeof(o));
+    const mxArray* s = nrhs > 2 ? prhs[2] : nullptr;
+    if (s) {
+      o.maxiter = (int32_t)field_or(s, "maxiter", 0);
+      o.maxinner = (int32_t)field_or(s, "maxinner", 0);
+      o.tolgradnorm = field_or(s, "tolgradnorm", 0);
+      o.use_graph = (int32_t)field_or(s, "use_graph", 1);
+    }
+    manisdp_tr_info info;
+    CK(h, manisdp_tr_solve(h, &o, &info), "tr_solve");
+    const char* names[] = {"cost", "gradnorm", "Delta", "seconds", "hv_count", "iters", "accepted", "stop_reason"};
+    const double vals[] = {info.cost, info.gradnorm, info.Delta, info.seconds, (double)info.hv_count,
+                           (double)info.iters, (double)info.accepted, (double)info.stop_reason};
+    plhs[0] = scalar_struct(names, vals, 8);
+  } else if (c == "kkt") {
+    manisdp_kkt_info k;
+    CK(h, manisdp_kkt(h, (int32_t)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), (int32_t)mxGetScalar(prhs[4]), &k), "kkt");
+    const char* names[] = {"obj", "by", "pinf", "dinf", "gap", "lam_min", "lam_max", "z_sum", "nneg", "eig_iters",
+                           "eig_resid"};
+    const double vals[] = {k.obj, k.by, k.pinf, k.dinf, k.gap, k.lam_min, k.lam_max, k.z_sum, (double)k.nneg,
+                           (double)k.eig_iters, k.eig_resid};
+    plhs[0] = scalar_struct(names, vals, 11);
+  } else if (c == "rank_cut") {
+    int64_t r = 0, p = 0;
+    CK(h, manisdp_rank_cut(h, mxGetScalar(prhs[2]), (int32_t)mxGetScalar(prhs[3]), &r, &p), "rank_cut");
+    plhs[0] = mxCreateDoubleScalar((double)r);
+    if (nlhs > 1) plhs[1] = mxCreateDoubleScalar((double)p);
+  } else if (c == "escape") {
+    CK(h, manisdp_escape(h, (int32_t)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), (int32_t)mxGetScalar(prhs[4])),
+       "escape");
+  } else if (c == "line_search") {
+    double a = 0;
+    CK(h, manisdp_line_search(h, &a), "line_search");
+    plhs[0] = mxCreateDoubleScalar(a);
+  } else if (c == "get_eigs") {
+    const int k = (int)mxGetScalar(prhs[2]);
+    CK(h, manisdp_get_stats(h, &st), "get_stats");
+    plhs[0] = mxCreateDoubleMatrix((mwSize)k, 1, mxREAL);
+    mxArray* V = mxCreateDoubleMatrix((mwSize)k, (mwSize)st.n, mxREAL);  // k x n column-major == n x k rows
+    CK(h, manisdp_get_eigs(h, mxGetPr(plhs[0]), mxGetPr(V), k), "get_eigs");
+    if (nlhs > 1)
+      plhs[1] = V;
+    else
+      mxDestroyArray(V);
+  } else if (c == "cost") {
+    double f = 0;
+    CK(h, manisdp_cost(h, &f), "cost");
+    plhs[0] = mxCreateDoubleScalar(f);
+  } else if (c == "grad") {
+    double gn = 0;
+    CK(h, manisdp_grad(h, &gn), "grad");
+    CK(h, manisdp_get_stats(h, &st), "get_stats");
+    plhs[0] = mxCreateDoubleMatrix((mwSize)st.p, (mwSize)st.n, mxREAL);
+    CK(h, manisdp_slot_get(h, MANISDP_SLOT_G, mxGetPr(plhs[0]), MANISDP_LAYOUT_ROWS), "slot_get");
+    if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(gn);
+  } else if (c == "hess") {
+    CK(h, manisdp_get_stats(h, &st), "get_stats");
+    CK(h, manisdp_slot_set(h, MANISDP_SLOT_U, mxGetPr(prhs[2]), MANISDP_LAYOUT_ROWS), "slot_set");
+    CK(h, manisdp_hess(h), "hess");
+    plhs[0] = mxCreateDoubleMatrix((mwSize)st.p, (mwSize)st.n, mxREAL);
+    CK(h, manisdp_slot_get(h, MANISDP_SLOT_H, mxGetPr(plhs[0]), MANISDP_LAYOUT_ROWS), "slot_get");
+  } else if (c == "stats") {
+    CK(h, manisdp_get_stats(h, &st), "get_stats");
+    const char* names[] = {"n", "m", "p", "nnzC", "nnzA", "s_mode", "a_mode", "hv_total", "launches_total",
+                           "bytes_per_hv", "flops_per_hv"};
+    const double vals[] = {(double)st.n, (double)st.m, (double)st.p, (double)st.nnzC, (double)st.nnzA,
+                           (double)st.s_mode, (double)st.a_mode, (double)st.hv_total, (double)st.launches_total,
+                           st.bytes_per_hv, st.flops_per_hv};
+    plhs[0] = scalar_struct(names, vals, 11);
+  } else {
+    mexErrMsgIdAndTxt("ManiSDP:b200:arg", "unknown command '%s'", cmd);
+  }
+}
