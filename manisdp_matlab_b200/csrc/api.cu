@@ -1,6 +1,7 @@
 // api.cu -- extern "C" surface of libmanisdp_b200.so (include/manisdp_b200.h): lifetime, state transfer, closures.
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include "affine.h"
 #include "dist.h"
@@ -179,6 +180,28 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
     if (ir[base + e] >= (uint64_t)nrows_global) return msdp_fail(h, MANISDP_E_ARG, "C: row index out of range");
     ci[(size_t)e] = (int)ir[base + e];
   }
+  // locality statistics for the column-blocking decision of spmm.cu
+  {
+    const char* em = getenv("MANISDP_SPMM_BLOCK");
+    if (em) h->spmm_block_mode = atoi(em);
+    const char* eb = getenv("MANISDP_SPMM_BULK");
+    if (eb) h->spmm_use_bulk = atoi(eb);
+    const char* el = getenv("MANISDP_L2_TARGET_MB");
+    if (el && atoi(el) > 0) h->spmm_l2_target = (int64_t)atoi(el) << 20;
+    const int64_t window = h->spmm_l2_target / (64 * 8);  // operand rows per L2 window at the nominal width p = 64
+    bool sorted = true;
+    uint64_t far = 0;
+    for (int64_t j = 0; j < ncols; ++j) {
+      const int64_t grow = h->row_begin + j;
+      for (int e = rp[(size_t)j]; e < rp[(size_t)j + 1]; ++e) {
+        if (e > rp[(size_t)j] && ci[(size_t)e] <= ci[(size_t)e - 1]) sorted = false;
+        const int64_t dlt = (int64_t)ci[(size_t)e] - grow;
+        if (dlt > window || dlt < -window) ++far;
+      }
+    }
+    h->C_sorted = sorted ? 1 : 0;
+    h->C_far_fraction = nnz ? (double)far / (double)nnz : 0.0;
+  }
   out.nrows = ncols;
   out.nnz = (int64_t)nnz;
   CUDA_TRY(h, cudaMalloc((void**)&out.rowptr, rp.size() * sizeof(int)));
@@ -262,6 +285,7 @@ static void free_all(manisdp_handle* h) {
   for (double* a : arrs)
     if (a) cudaFree(a);
   if (h->C.rowptr) cudaFree(h->C.rowptr);
+  if (h->spmm_bptr) cudaFree(h->spmm_bptr);
   if (h->C.col) cudaFree(h->C.col);
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);

@@ -124,6 +124,15 @@ struct manisdp_handle {
   int tcg_graph_maxinner = -1;
   double graph_sigma = -1.0;
   int64_t graph_l_fixed = 0, graph_l_body = 0;  // kernels per graph launch: outside / inside the WHILE body
+  // column-blocked SpMM (spmm.cu): pass pointers for the current operand width
+  int spmm_ld = -1, spmm_B = 1;
+  int* spmm_bptr = nullptr;
+  size_t spmm_bptr_cap = 0;
+  int spmm_use_bulk = 1;               // 1: cp.async.bulk gather kernel for ld >= 32 ; 0: register gathers only
+  int spmm_block_mode = 0;             // 0 never (default), 1 auto (only for matrices without locality), 2 always
+  int64_t spmm_l2_target = 64ll << 20; // bytes of operand rows per column block
+  int C_sorted = 0;                    // rows of C are column-sorted
+  double C_far_fraction = 0.0;         // share of entries whose column is farther than an L2 window from the row
   // NCCL
   void* nccl_comm = nullptr;
   std::string err;

@@ -1,17 +1,34 @@
 // spmm.cu -- K1: CSR SpMM with fused row epilogues, the closures of ManiSDP_onlyunitdiag.m:117-130.
 //
-//   hess      (:128-129)  eH = U*C ; H = eH - Y.*sum(Y.*eH) - U.*eG          -> one kernel, + <U,H> for tCG.m:166
-//   cost+grad (:118-124)  YC = Y*C ; eG = sum(YC.*Y) ; f = .5*sum(eG) ; G = YC - Y.*eG   -> one kernel, + |G|^2
-//   S*V       (:49)       (C - diag(z)) * V for the eigen step                -> one kernel
+//   hess      (:128-129)  eH = U*C ; H = eH - Y.*sum(Y.*eH) - U.*eG          -> + <U,H> for tCG.m:166
+//   cost+grad (:118-124)  YC = Y*C ; eG = sum(YC.*Y) ; f = .5*sum(eG) ; G = YC - Y.*eG   -> + |G|^2
+//   S*V       (:49)       (C - diag(z)) * V for the eigen step
 //
 // Layout: the factor is vertex-major (row i = the p numbers of vertex i, ld = 4*ceil(p/4) doubles = the reference's
-// p x n column-major array), so one gathered operand row is one contiguous ld*8-byte segment.  A row of the output is
-// produced by a group of GS lanes, each holding VPL double2 accumulators; the row's (col, val) entries are loaded
-// coalesced by the group and broadcast with shuffles; gathers are issued four at a time for memory-level parallelism.
-// The row epilogue (projection onto the tangent space of the oblique manifold, ManiSDP_onlyunitdiag.m:138-139) needs
-// only the finished row, so it is fused and H is written exactly once.
+// p x n column-major array), so one gathered operand row is one contiguous ld*8-byte segment.  The row epilogue
+// (projection onto the tangent space of the oblique manifold, ManiSDP_onlyunitdiag.m:138-139) needs only the finished
+// row, so it is fused and H is written exactly once.
+//
+// Two inner loops:
+//   k_spmm_bulk (ld >= 32, one warp per row): operand rows are fetched with cp.async.bulk (the TMA engine's 1-D bulk
+//     copy, SASS UBLKCP) into a per-warp shared-memory ring of 2 x SLOTS rows completed through mbarriers, so the
+//     gathers in flight are bounded by shared memory (192 KB/SM = 384 rows of 512 B) instead of registers; the next
+//     batch is issued before the current one is consumed and the row pointers are read one row ahead.
+//   k_spmm (any ld, GS lanes per row): register gathers, four in flight per group; used for thin blocks (eigen step,
+//     small p) where a full warp per row would idle.
+//
+// Round-1 measurements that shaped this (profiles/): on the n = 1e6 Erdos-Renyi instance the product needs
+// nnz*p*8 = 25 GB of gathers against 2.1 GB of compulsory bytes and the operand (512 MB) is 4x the L2, so ncu shows
+// 22.6 GB of DRAM reads per launch; random 512 B gathers reach 7.7 TB/s from a 512 MB table and 19 TB/s from an
+// L2-resident one (r1_gather_microbench.jsonl).  COLUMN PASSES (B > 1: pass b adds the entries with col in block b to
+// the partial rows kept in `out`, the last pass applies the epilogue) cut the DRAM traffic to ~10 GB but are latency
+// bound per pass in this form (tools/spmm_lab.cu: best 3.18 ms at B = 4 vs 3.33 ms at B = 1), so they stay opt-in
+// (MANISDP_SPMM_BLOCK) until the per-pass pipeline is deeper.
 //
 // Algorithmic bytes per product: 12*nnz + 4*(n+1) + 24*n*p + 8*n.
+#include <algorithm>
+#include <vector>
+#include "dist.h"
 #include "rowops.cuh"
 #include "scalar_logic.cuh"
 #include "kernels.cuh"
@@ -19,11 +36,14 @@
 enum { EPI_HESS = 0, EPI_COSTGRAD = 1, EPI_SHIFT = 2 };
 
 struct SpmmArgs {
-  const int* rowptr;
   const int* col;
   const double* val;
+  const int* bptr0;    // per row: first entry of this pass
+  const int* bptr1;    // per row: one past the last entry of this pass
+  int first, last;     // first pass: accumulators start at 0 ; last pass: epilogue + reductions
   int64_t nrows;
   int ld;
+  int slots;           // bulk kernel: rows per ring buffer
   const double* Ug;    // gather source, indexed by GLOBAL row
   const double* Uown;  // the same array restricted to the owned rows (local row index)
   const double* Y;     // point, owned rows
@@ -39,39 +59,169 @@ struct SpmmArgs {
   int mode;            // tail_mode (EPI_HESS) or cg_mode (EPI_COSTGRAD)
 };
 
-template <int GS, int VPL, int EPI>
-__global__ void __launch_bounds__(MSDP_THREADS) k_spmm(SpmmArgs a) {
-  __shared__ double sm[2 * 32];
-  RtrState* st = a.st;
-  if (EPI == EPI_HESS && a.mode != TAIL_NONE && st->stop != 0) return;
-  // ---- device-side buffer selection (no host round trip between TR iterations)
+struct SpmmPtrs {
+  const double *Y, *eG, *Uown, *Ug;
+  double *out, *eGout;
+};
+
+// device-side buffer selection (no host round trip between TR iterations)
+__device__ __forceinline__ SpmmPtrs select_ptrs(const SpmmArgs& a) {
+  SpmmPtrs p{a.Y, a.eG, a.Uown, a.Ug, a.out, a.eGout};
   if (a.sel == 1) {
-    const int pt = st->pt;
-    a.Y = pt ? a.v.Y1 : a.v.Y0;
-    a.eG = pt ? a.v.eG1 : a.v.eG0;
+    const int pt = a.st->pt;
+    p.Y = pt ? a.v.Y1 : a.v.Y0;
+    p.eG = pt ? a.v.eG1 : a.v.eG0;
   } else if (a.sel >= 2) {
-    const int w = (a.sel == 2) ? (st->pt ^ 1) : st->pt;
-    a.Uown = w ? a.v.Y1 : a.v.Y0;
-    if (!a.sharded) a.Ug = a.Uown;
-    a.out = w ? a.v.G1 : a.v.G0;
-    a.eGout = w ? a.v.eG1 : a.v.eG0;
+    const int w = (a.sel == 2) ? (a.st->pt ^ 1) : a.st->pt;
+    p.Uown = w ? a.v.Y1 : a.v.Y0;
+    if (!a.sharded) p.Ug = p.Uown;
+    p.out = w ? a.v.G1 : a.v.G0;
+    p.eGout = w ? a.v.eG1 : a.v.eG0;
   }
-  const int* __restrict__ rowptr = a.rowptr;
+  return p;
+}
+
+__device__ __forceinline__ double2 ldcs2(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void stcs2(double* p, double2 v) { __stcs(reinterpret_cast<double2*>(p), v); }
+
+// fused row epilogue on the finished accumulators of one row (lane holds vectors gl + GS*t)
+template <int GS, int VPL, int EPI>
+__device__ __forceinline__ void row_epilogue(double2 (&acc)[VPL], const SpmmPtrs& p, int64_t row, int ld, int gl,
+                                             unsigned mask, double (&q)[2]) {
+  const int nvec = ld / 2;
+  const size_t rb = (size_t)row * ld;
+  if (EPI == EPI_HESS) {
+    double2 y[VPL], u[VPL];
+    double dot = 0.0;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int cv = gl + GS * t;
+      if (cv < nvec) {
+        y[t] = ld2(p.Y + rb + 2 * cv);
+        u[t] = ld2(p.Uown + rb + 2 * cv);
+        dot += y[t].x * acc[t].x + y[t].y * acc[t].y;
+      }
+    }
+    dot = group_sum<GS>(dot, mask);  // sum(Y.*eH), :129
+    const double eg = p.eG[row];
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int cv = gl + GS * t;
+      if (cv < nvec) {
+        double2 hv;
+        hv.x = acc[t].x - y[t].x * dot - u[t].x * eg;
+        hv.y = acc[t].y - y[t].y * dot - u[t].y * eg;
+        st2(p.out + rb + 2 * cv, hv);
+        q[0] += u[t].x * hv.x + u[t].y * hv.y;  // <mdelta, Hmdelta>, tCG.m:166
+      }
+    }
+  } else if (EPI == EPI_COSTGRAD) {
+    double2 y[VPL];
+    double dot = 0.0;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int cv = gl + GS * t;
+      if (cv < nvec) {
+        y[t] = ld2(p.Uown + rb + 2 * cv);
+        dot += y[t].x * acc[t].x + y[t].y * acc[t].y;
+      }
+    }
+    dot = group_sum<GS>(dot, mask);  // eG(row) = sum(YC.*Y), :119
+    if (gl == 0) {
+      p.eGout[row] = dot;
+      q[0] += dot;
+    }
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int cv = gl + GS * t;
+      if (cv < nvec) {
+        double2 g;
+        g.x = acc[t].x - y[t].x * dot;  // G = YC - Y.*eG, :124
+        g.y = acc[t].y - y[t].y * dot;
+        st2(p.out + rb + 2 * cv, g);
+        q[1] += g.x * g.x + g.y * g.y;
+      }
+    }
+  } else {  // EPI_SHIFT: out = C*V - z.*V
+    const double z = p.eG ? p.eG[row] : 0.0;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int cv = gl + GS * t;
+      if (cv < nvec) {
+        const double2 u = ld2(p.Uown + rb + 2 * cv);
+        double2 o;
+        o.x = acc[t].x - z * u.x;
+        o.y = acc[t].y - z * u.y;
+        st2(p.out + rb + 2 * cv, o);
+      }
+    }
+  }
+}
+
+// grid reductions + scalar logic of the last pass
+template <int EPI>
+__device__ __forceinline__ void spmm_tail(const SpmmArgs& a, double (&q)[2], double* sm) {
+  RtrState* st = a.st;
+  if (EPI == EPI_HESS) {
+    if (a.mode == TAIL_NONE) return;
+    double tot[1], q1[1] = {q[0]};
+    __syncwarp();
+    if (grid_sum_last<1>(q1, a.partials, &st->ticket, sm, tot)) {
+      if (threadIdx.x == 0) {
+        if (a.mode == TAIL_TCG)
+          tcg_after_hv(st, tot[0]);
+        else
+          st->tmp[0] = tot[0];
+      }
+    }
+  } else if (EPI == EPI_COSTGRAD) {
+    double tot[2];
+    __syncwarp();
+    if (grid_sum_last<2>(q, a.partials, &st->ticket, sm, tot)) {
+      if (threadIdx.x == 0) {
+        const double f = 0.5 * tot[0];  // :120
+        st->tmp[0] = f;
+        st->tmp[1] = tot[1];
+        if (a.mode == CG_INIT) {
+          st->fx = f;
+          st->gradnorm2 = tot[1];
+        } else if (a.mode == CG_TR) {
+          st->fprop = f;
+          st->gradnorm2_prop = tot[1];
+          tr_decide(st);
+        } else if (a.mode == CG_TR_DEFER) {
+          st->tmp[0] = tot[0];  // un-halved local sum; the scalar kernel halves after the all-reduce
+        }
+      }
+    }
+  }
+}
+
+// ---- register-gather kernel (any ld) --------------------------------------------------------------------------------
+template <int GS, int VPL, int EPI>
+__global__ void __launch_bounds__(MSDP_THREADS) k_spmm(const SpmmArgs a) {
+  __shared__ double sm[2 * 32];
+  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  const SpmmPtrs p = select_ptrs(a);
   const int* __restrict__ col = a.col;
   const double* __restrict__ val = a.val;
-  const double* __restrict__ Ug = a.Ug;
+  const double* __restrict__ Ug = p.Ug;
   const int ld = a.ld, nvec = ld / 2;
   const unsigned mask = group_mask<GS>();
   const int gl = threadIdx.x % GS;
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
+  const bool first = a.first != 0, last = a.last != 0;
   double q[2] = {0.0, 0.0};
 
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; row < a.nrows; row += ngroups) {
-    const int e0 = rowptr[row], e1 = rowptr[row + 1];
+    const int e0 = __ldg(a.bptr0 + row), e1 = __ldg(a.bptr1 + row);
+    const size_t rb = (size_t)row * ld;
     double2 acc[VPL];
 #pragma unroll
-    for (int t = 0; t < VPL; ++t) acc[t] = make_double2(0.0, 0.0);
-
+    for (int t = 0; t < VPL; ++t) {
+      const int cv = gl + GS * t;
+      acc[t] = (!first && cv < nvec) ? ldcs2(p.out + rb + 2 * cv) : make_double2(0.0, 0.0);
+    }
     for (int base = e0; base < e1; base += GS) {
       const int e = base + gl;
       int c = 0;
@@ -123,110 +273,158 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_spmm(SpmmArgs a) {
         }
       }
     }
+    if (!last) {  // partial rows of an inner pass: streamed back, re-read by the next pass
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) {
+        const int cv = gl + GS * t;
+        if (cv < nvec) stcs2(p.out + rb + 2 * cv, acc[t]);
+      }
+      continue;
+    }
+    row_epilogue<GS, VPL, EPI>(acc, p, row, ld, gl, mask, q);
+  }
+  if (last) spmm_tail<EPI>(a, q, sm);
+}
 
-    // ---- fused row epilogue
+// ---- bulk-async gather kernel (ld >= 32, one warp per row) ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+#define BULK_WARPS 8
+#define BULK_MAXSLOTS 8
+
+template <int VPL, int EPI>
+__global__ void __launch_bounds__(BULK_WARPS * 32) k_spmm_bulk(const SpmmArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ double sm[2 * 32];
+  __shared__ uint64_t bars[BULK_WARPS * 2];
+  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  const SpmmPtrs p = select_ptrs(a);
+  const int* __restrict__ col = a.col;
+  const double* __restrict__ val = a.val;
+  const double* __restrict__ Ug = p.Ug;
+  const int ld = a.ld, nvec = ld / 2, slots = a.slots;
+  const uint32_t rowbytes = (uint32_t)ld * 8u;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* myring = reinterpret_cast<double*>(smraw) + (size_t)wid * 2 * slots * ld;
+  uint64_t* mybar = bars + wid * 2;
+  if (lane == 0) {
+    mbar_init(&mybar[0], 1);
+    mbar_init(&mybar[1], 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const bool first = a.first != 0, last = a.last != 0;
+  const int64_t nw = (int64_t)gridDim.x * BULK_WARPS;
+  int64_t row = (int64_t)blockIdx.x * BULK_WARPS + wid;
+  uint32_t it = 0;  // batch counter of this warp: buffer = it & 1, parity = (it >> 1) & 1
+  double q[2] = {0.0, 0.0};
+  int e0 = 0, e1 = 0;
+  if (row < a.nrows) {
+    e0 = __ldg(a.bptr0 + row);
+    e1 = __ldg(a.bptr1 + row);
+  }
+  for (; row < a.nrows; row += nw) {
+    const int64_t rown = row + nw;
+    int e0n = 0, e1n = 0;
+    if (rown < a.nrows) {  // row pointers one row ahead
+      e0n = __ldg(a.bptr0 + rown);
+      e1n = __ldg(a.bptr1 + rown);
+    }
     const size_t rb = (size_t)row * ld;
-    if (EPI == EPI_HESS) {
-      double2 y[VPL], u[VPL];
-      double dot = 0.0;
+    double2 acc[VPL];
 #pragma unroll
-      for (int t = 0; t < VPL; ++t) {
-        const int cv = gl + GS * t;
-        if (cv < nvec) {
-          y[t] = ld2(a.Y + rb + 2 * cv);
-          u[t] = ld2(a.Uown + rb + 2 * cv);
-          dot += y[t].x * acc[t].x + y[t].y * acc[t].y;
-        }
-      }
-      dot = group_sum<GS>(dot, mask);  // sum(Y.*eH), :129
-      const double eg = a.eG[row];
-#pragma unroll
-      for (int t = 0; t < VPL; ++t) {
-        const int cv = gl + GS * t;
-        if (cv < nvec) {
-          double2 hv;
-          hv.x = acc[t].x - y[t].x * dot - u[t].x * eg;
-          hv.y = acc[t].y - y[t].y * dot - u[t].y * eg;
-          st2(a.out + rb + 2 * cv, hv);
-          q[0] += u[t].x * hv.x + u[t].y * hv.y;  // <mdelta, Hmdelta>, tCG.m:166
-        }
-      }
-    } else if (EPI == EPI_COSTGRAD) {
-      double2 y[VPL];
-      double dot = 0.0;
-#pragma unroll
-      for (int t = 0; t < VPL; ++t) {
-        const int cv = gl + GS * t;
-        if (cv < nvec) {
-          y[t] = ld2(a.Uown + rb + 2 * cv);
-          dot += y[t].x * acc[t].x + y[t].y * acc[t].y;
-        }
-      }
-      dot = group_sum<GS>(dot, mask);  // eG(row) = sum(YC.*Y), :119
-      if (gl == 0) {
-        a.eGout[row] = dot;
-        q[0] += dot;
-      }
-#pragma unroll
-      for (int t = 0; t < VPL; ++t) {
-        const int cv = gl + GS * t;
-        if (cv < nvec) {
-          double2 g;
-          g.x = acc[t].x - y[t].x * dot;  // G = YC - Y.*eG, :124
-          g.y = acc[t].y - y[t].y * dot;
-          st2(a.out + rb + 2 * cv, g);
-          q[1] += g.x * g.x + g.y * g.y;
-        }
-      }
-    } else {  // EPI_SHIFT: out = C*V - z.*V
-      const double z = a.eG ? a.eG[row] : 0.0;
-#pragma unroll
-      for (int t = 0; t < VPL; ++t) {
-        const int cv = gl + GS * t;
-        if (cv < nvec) {
-          const double2 u = ld2(a.Uown + rb + 2 * cv);
-          double2 o;
-          o.x = acc[t].x - z * u.x;
-          o.y = acc[t].y - z * u.y;
-          st2(a.out + rb + 2 * cv, o);
-        }
-      }
+    for (int t = 0; t < VPL; ++t) {
+      const int cv = lane + 32 * t;
+      acc[t] = (!first && cv < nvec) ? ldcs2(p.out + rb + 2 * cv) : make_double2(0.0, 0.0);
     }
+    int pos = e0;
+    int c = 0;
+    double w = 0.0;
+    int nb = min(slots, e1 - pos);
+    if (nb > 0) {
+      if (lane < nb) {
+        c = __ldcs(col + pos + lane);
+        w = __ldcs(val + pos + lane);
+      }
+      if (lane == 0) mbar_expect_tx(&mybar[it & 1], (uint32_t)nb * rowbytes);
+      __syncwarp();
+      if (lane < nb)
+        bulk_g2s(myring + ((size_t)(it & 1) * slots + lane) * ld, Ug + (size_t)c * ld, rowbytes, &mybar[it & 1]);
+    }
+    while (nb > 0) {
+      const int posn = pos + nb;
+      const int nbn = min(slots, e1 - posn);
+      int cn = 0;
+      double wn = 0.0;
+      if (nbn > 0) {  // issue the next batch before consuming the current one
+        if (lane < nbn) {
+          cn = __ldcs(col + posn + lane);
+          wn = __ldcs(val + posn + lane);
+        }
+        if (lane == 0) mbar_expect_tx(&mybar[(it + 1) & 1], (uint32_t)nbn * rowbytes);
+        __syncwarp();
+        if (lane < nbn)
+          bulk_g2s(myring + ((size_t)((it + 1) & 1) * slots + lane) * ld, Ug + (size_t)cn * ld, rowbytes,
+                   &mybar[(it + 1) & 1]);
+      }
+      mbar_wait(&mybar[it & 1], (it >> 1) & 1);
+      const double* slot = myring + (size_t)(it & 1) * slots * ld;
+#pragma unroll
+      for (int s = 0; s < BULK_MAXSLOTS; ++s) {
+        if (s < nb) {
+          const double ws = __shfl_sync(0xffffffffu, w, s);
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) {
+            const int cv = lane + 32 * t;
+            if (cv < nvec) {
+              const double2 u = ld2(slot + (size_t)s * ld + 2 * cv);
+              acc[t].x = fma(ws, u.x, acc[t].x);
+              acc[t].y = fma(ws, u.y, acc[t].y);
+            }
+          }
+        }
+      }
+      __syncwarp();  // every lane has read the slots before they are refilled
+      ++it;
+      pos = posn;
+      nb = nbn;
+      c = cn;
+      w = wn;
+    }
+    if (!last) {
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) {
+        const int cv = lane + 32 * t;
+        if (cv < nvec) stcs2(p.out + rb + 2 * cv, acc[t]);
+      }
+    } else {
+      row_epilogue<32, VPL, EPI>(acc, p, row, ld, lane, 0xffffffffu, q);
+    }
+    e0 = e0n;
+    e1 = e1n;
   }
-
-  if (EPI == EPI_HESS) {
-    if (a.mode == TAIL_NONE) return;
-    double tot[1], q1[1] = {q[0]};
-    __syncwarp();
-    if (grid_sum_last<1>(q1, a.partials, &st->ticket, sm, tot)) {
-      if (threadIdx.x == 0) {
-        if (a.mode == TAIL_TCG)
-          tcg_after_hv(st, tot[0]);
-        else
-          st->tmp[0] = tot[0];
-      }
-    }
-  } else if (EPI == EPI_COSTGRAD) {
-    double tot[2];
-    __syncwarp();
-    if (grid_sum_last<2>(q, a.partials, &st->ticket, sm, tot)) {
-      if (threadIdx.x == 0) {
-        const double f = 0.5 * tot[0];  // :120
-        st->tmp[0] = f;
-        st->tmp[1] = tot[1];
-        if (a.mode == CG_INIT) {
-          st->fx = f;
-          st->gradnorm2 = tot[1];
-        } else if (a.mode == CG_TR) {
-          st->fprop = f;
-          st->gradnorm2_prop = tot[1];
-          tr_decide(st);
-        } else if (a.mode == CG_TR_DEFER) {
-          st->tmp[0] = tot[0];  // un-halved local sum; the scalar kernel halves after the all-reduce
-        }
-      }
-    }
-  }
+  if (last) spmm_tail<EPI>(a, q, sm);
 }
 
 __global__ void k_tr_decide_scalar(RtrState* st) {
@@ -249,19 +447,108 @@ int msdp_launch_tcg_after_hv_scalar(manisdp_handle* h) {
   return MANISDP_OK;
 }
 
-template <int EPI>
-static int launch_spmm(manisdp_handle* h, const SpmmArgs& a) {
-  DISPATCH_GEOM(row_geom(a.ld), {
-    const int nb = rows_grid(h, a.nrows, GS);
-    k_spmm<GS, VPL, EPI><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
-  });
+// ---- column passes ------------------------------------------------------------------------------------------------------
+// bptr[b*nrows + row] = first entry of `row` whose column is >= b*jrows  (b = 0..B); rows must be column-sorted
+__global__ void k_block_ptrs(const int* __restrict__ rowptr, const int* __restrict__ col, int64_t nrows, int64_t jrows,
+                             int B, int* __restrict__ bptr) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (int64_t)gridDim.x * blockDim.x) {
+    const int e0 = rowptr[row], e1 = rowptr[row + 1];
+    int e = e0;
+    for (int b = 0; b <= B; ++b) {
+      const int64_t lim = (int64_t)b * jrows;
+      while (e < e1 && col[e] < lim) ++e;
+      bptr[(size_t)b * nrows + row] = (b == B) ? e1 : e;
+    }
+  }
+}
+
+// decide the number of column passes for operand rows of `ld` doubles and (re)build the pass pointers
+int msdp_spmm_prepare(manisdp_handle* h, int ld) {
+  if (h->spmm_ld == ld) return MANISDP_OK;
+  h->spmm_ld = ld;
+  h->spmm_B = 1;
+  const int64_t ncols = (h->world > 1) ? msdp_rows_per_rank(h->n, h->world) * h->world : h->n;
+  const double operand_bytes = (double)ncols * ld * 8.0;
+  int B = 1;
+  if (h->spmm_block_mode != 0 && h->C_sorted && operand_bytes > (double)h->spmm_l2_target * 1.5) {
+    if (h->spmm_block_mode == 2 || h->C_far_fraction > 0.3) {
+      B = (int)((operand_bytes + h->spmm_l2_target - 1) / h->spmm_l2_target);
+      if (B > 64) B = 64;
+    }
+  }
+  if (B <= 1) return MANISDP_OK;
+  const int64_t jrows = (ncols + B - 1) / B;
+  if (h->spmm_bptr_cap < (size_t)(B + 1) * (size_t)h->nloc) {
+    if (h->spmm_bptr) cudaFree(h->spmm_bptr);
+    h->spmm_bptr = nullptr;
+    h->spmm_bptr_cap = (size_t)(B + 1) * (size_t)h->nloc;
+    CUDA_TRY(h, cudaMalloc((void**)&h->spmm_bptr, h->spmm_bptr_cap * sizeof(int)));
+  }
+  k_block_ptrs<<<std::max(1, (int)std::min<int64_t>(h->num_sms * 8, (h->nloc + 255) / 256)), 256, 0, h->stream>>>(
+      h->C.rowptr, h->C.col, h->nloc, jrows, B, h->spmm_bptr);
   KERNEL_CHECK(h);
+  h->spmm_B = B;
+  return MANISDP_OK;
+}
+
+template <int VPL, int EPI>
+static int launch_bulk(manisdp_handle* h, const SpmmArgs& a) {
+  const size_t smem = (size_t)BULK_WARPS * 2 * a.slots * a.ld * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_spmm_bulk<VPL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
+  const int64_t rows_per_block = BULK_WARPS;
+  int64_t nb = (a.nrows + rows_per_block - 1) / rows_per_block;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
+  nb = std::min<int64_t>(nb, (int64_t)h->num_sms * per_sm);
+  nb = std::min<int64_t>(std::max<int64_t>(nb, 1), MSDP_MAX_BLOCKS);
+  k_spmm_bulk<VPL, EPI><<<(int)nb, BULK_WARPS * 32, smem, h->stream>>>(a);
+  return MANISDP_OK;
+}
+
+template <int EPI>
+static int launch_spmm(manisdp_handle* h, SpmmArgs a) {
+  MSDP_TRY(msdp_spmm_prepare(h, a.ld));
+  const int B = h->spmm_B;
+  // bulk path: measured on B200 (profiles/r1_sweep_bulk_vs_regs.txt) it wins from ld = 128 on (7.7 vs 10.2 ms at
+  // p = 128), ties at p = 64 and loses below, where four register gathers per group already cover the latency
+  const bool bulk = h->spmm_use_bulk == 2 ? (a.ld >= 32) : (h->spmm_use_bulk == 1 && a.ld >= 96);
+  a.slots = std::max(1, std::min(BULK_MAXSLOTS, 4096 / (a.ld * 8)));
+  for (int b = 0; b < B; ++b) {
+    if (B == 1) {
+      a.bptr0 = h->C.rowptr;
+      a.bptr1 = h->C.rowptr + 1;
+    } else {
+      a.bptr0 = h->spmm_bptr + (size_t)b * h->nloc;
+      a.bptr1 = h->spmm_bptr + (size_t)(b + 1) * h->nloc;
+    }
+    a.first = (b == 0);
+    a.last = (b == B - 1);
+    if (bulk) {
+      const int vpl = row_geom(a.ld).vpl;
+      if (vpl == 1)
+        launch_bulk<1, EPI>(h, a);
+      else if (vpl == 2)
+        launch_bulk<2, EPI>(h, a);
+      else if (vpl == 4)
+        launch_bulk<4, EPI>(h, a);
+      else
+        launch_bulk<8, EPI>(h, a);
+    } else {
+      DISPATCH_GEOM(row_geom(a.ld), {
+        const int nb = rows_grid(h, a.nrows, GS);
+        k_spmm<GS, VPL, EPI><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+      });
+    }
+    KERNEL_CHECK(h);
+  }
   return MANISDP_OK;
 }
 
 static SpmmArgs base_args(manisdp_handle* h) {
   SpmmArgs a{};
-  a.rowptr = h->C.rowptr;
   a.col = h->C.col;
   a.val = h->C.val;
   a.nrows = h->nloc;
