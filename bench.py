@@ -265,6 +265,11 @@ def run_ours(args, rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = st.bytes_per_hv / (ms * 1e-3) / 1e9
+    if args.traffic is None and world == 1 and args.workload == "er" and args.n == 1_000_000 and p == 64:
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+            args.traffic = float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_spmm_hess_er_p64"])
+        except Exception:
+            pass
     roofline = {"kernel": "k_spmm<GS,VPL,EPI_HESS> (CSR SpMM + oblique tangent projection, fused)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
@@ -272,6 +277,9 @@ def run_ours(args, rank, world):
                 "ms_per_launch": ms, "gflops": st.flops_per_hv / (ms * 1e-3) / 1e9,
                 "includes_allgather": world > 1}
     h.close()
+    secondary = None
+    if world == 1 and args.workload == "er" and not args.no_secondary:
+        secondary = torus_secondary(args, peak)
     if rank != 0:
         return
     # ---- CPU baseline (bounded sample) + config-1 time-to-KKT ----------------------------------------------------
@@ -294,8 +302,34 @@ def run_ours(args, rank, world):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(Y0.nbytes),
                     "d2h_bytes_per_step": int(out_host.nbytes) + 256, "steps": ne},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "setup_s": {"generate": t_gen, "create": t_create}, "kkt": kkt}
+            "setup_s": {"generate": t_gen, "create": t_create}, "kkt": kkt, "secondary": secondary}
     print(json.dumps(line), flush=True)
+
+
+def torus_secondary(args, peak):
+    """Secondary profile of config 5: 1000 x 1000 torus, +-1 weights (G11/G32/G81 shape), same kernel."""
+    from manisdp_matlab_b200 import Handle, _lib, problems as P
+    side = int(round(args.n ** 0.5))
+    n, ei, ej, w = P.synthetic_torus(side, seed=0)
+    C = P.maxcut_C(n, ei, ej, w)
+    with Handle("onlyunitdiag", n, C_csc=C) as h:
+        h.set_Y(start_point(n, args.p))
+        h.slot_set(_lib.SLOT_U, np.random.default_rng(1).standard_normal((n, args.p)))
+        h.hess_bench(3)
+        ms = h.hess_bench(args.hv_reps)
+        st = h.stats()
+        hv, secs = 0, 0.0
+        for _ in range(3):
+            h.tr_solve(maxiter=1, maxinner=args.inner, tolgradnorm=1e-12, use_graph=args.graph)
+        for _ in range(5):
+            i = h.tr_solve(maxiter=1, maxinner=args.inner, tolgradnorm=1e-12, use_graph=args.graph)
+            hv += i.hv_count
+            secs += i.seconds
+    ach = st.bytes_per_hv / (ms * 1e-3) / 1e9
+    return {"workload": f"synthetic MaxCut {side}x{side} torus +-1 weights (G11/G32 profile), p={args.p}",
+            "nnzC": int(C.nnz), "value": hv / secs, "unit": UNIT,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_launch": st.bytes_per_hv, "ms_per_launch": ms}}
 
 
 def time_to_kkt():
@@ -338,6 +372,7 @@ def main():
     ap.add_argument("--ref-inner", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kkt", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

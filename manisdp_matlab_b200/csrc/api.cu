@@ -101,6 +101,7 @@ int msdp_resize(manisdp_handle* h, int64_t p) {
     msdp_invalidate_graph(h);
   }
   if (p != h->p) msdp_invalidate_graph(h);
+  h->y_version++;
   h->p = p;
   h->ld = ld;
   h->cache_valid = 0;
@@ -371,7 +372,10 @@ int manisdp_slot_set(manisdp_t* h, int32_t slot, const double* src, int32_t layo
   double* dst = slot_ptr(h, slot);
   if (!dst) return msdp_fail(h, MANISDP_E_ARG, "bad slot");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  if (slot == MANISDP_SLOT_Y) h->cache_valid = h->grad_valid = 0;
+  if (slot == MANISDP_SLOT_Y) {
+    h->cache_valid = h->grad_valid = 0;
+    h->y_version++;
+  }
   return upload_rows(h, dst, src, layout);
 }
 

@@ -116,6 +116,7 @@ struct manisdp_handle {
   // log + stats
   std::vector<manisdp_tr_iter> log;
   int64_t hv_total = 0, launches = 0;
+  int64_t y_version = 0;                 // bumped whenever the current point may have changed (rank-step cache key)
   int num_sms = 148;
   // CUDA graph cache for the tCG loop
   cudaGraphExec_t tcg_exec[2] = {nullptr, nullptr};  // one per value of pt (which buffer is the current point)

@@ -301,8 +301,9 @@ static int apply_S(manisdp_handle* h, EigWork& w, const double* V, double* AV, d
 // ---- LOBPCG ------------------------------------------------------------------------------------------------------------
 // Smallest (want_largest = 0) or largest (= 1) `nwant` eigenpairs of S.  Block size k >= nwant.  Results: vals[0..k),
 // w.X (n x kld) Ritz vectors, resid = max residual norm over the wanted pairs.
-static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, double tol_abs, int maxit, int warm,
-                  std::vector<double>& vals, double* resid_out, int* iters_out) {
+// Converged when the largest residual norm of the wanted pairs is <= max(tol_abs, tol_rel * max|theta|).
+static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, double tol_abs, double tol_rel, int maxit,
+                  int warm, std::vector<double>& vals, double* resid_out, int* iters_out) {
   const int k = w.k, kld = w.kld, nb = 3 * kld, nent = nb * nb;
   const int64_t n = h->nloc;
   const double sgn = want_largest ? -1.0 : 1.0;
@@ -329,6 +330,7 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
   MSDP_TRY(apply_S(h, w, w.X, w.AX, sgn));
 
   std::vector<double> G, GA, theta(kld, 0.0), norms(kld, 0.0);
+  std::vector<std::vector<double>> hist;
   std::vector<int> act_w, act_p;  // active column indices
   bool haveW = false, haveP = false;
   double resid = INFINITY;
@@ -352,8 +354,20 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
         if (norms[c] > tol_abs * 0.1 && norms[c] == norms[c]) act_w.push_back(c);
       }
       if (resid != resid) return msdp_fail(h, MANISDP_E_NUMERIC, "lobpcg: NaN residual");
-      if (resid <= tol_abs || it == maxit) break;
+      double tmax = 0.0;
+      for (int c = 0; c < nwant; ++c) tmax = std::max(tmax, fabs(vals[c]));
+      const double tol_now = std::max(tol_abs, tol_rel * tmax);
+      if (resid <= tol_now || it == maxit) break;
       if (act_w.empty()) break;
+      // Ritz values converge quadratically in the residual: stop when the wanted ones have stopped moving
+      // (change over the last 10 iterations below a tenth of the tolerance) although the residual test is not met
+      hist.push_back(std::vector<double>(vals.begin(), vals.begin() + nwant));
+      if (hist.size() > 10) {
+        const std::vector<double>& old = hist[hist.size() - 11];
+        double moved = 0.0;
+        for (int c = 0; c < nwant; ++c) moved = std::max(moved, fabs(old[c] - vals[c]));
+        if (moved <= 0.1 * tol_now) break;
+      }
     }
     // basis index list: X (all k), active W, active P
     std::vector<int> idx;
@@ -365,13 +379,15 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
       for (int c : act_w) {
         if (hG[(size_t)(2 * kld + c) * nb + (2 * kld + c)] > 0.0) act_p.push_back(c);
       }
+    // Rayleigh-Ritz on span[X, W_active, P_active] by canonical orthogonalisation: the unit-diagonal Gram matrix Gs is
+    // eigen-decomposed and only directions with eigenvalue > 1e-10 * max are kept, so a nearly dependent W or P column
+    // costs one direction instead of the whole block (a plain Cholesky here either fails or amplifies rounding).
     bool solved = false;
     std::vector<double> Cfull;  // nbasis x k coefficients w.r.t. the unscaled basis columns
     std::vector<double> ritz;
-    for (int attempt = 0; attempt < 2 && !solved; ++attempt) {
+    {
       std::vector<int> bidx = idx;
-      if (attempt == 0)
-        for (int c : act_p) bidx.push_back(2 * kld + c);
+      for (int c : act_p) bidx.push_back(2 * kld + c);
       const int m = (int)bidx.size();
       std::vector<double> dscale(m);
       for (int a = 0; a < m; ++a) {
@@ -386,43 +402,51 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
           Gs[(size_t)a * m + b] = g * dscale[a] * dscale[b];
           As[(size_t)a * m + b] = sgn * ga * dscale[a] * dscale[b];
         }
-      std::vector<double> L = Gs;
-      if (!cholesky(L, m, 1e-12)) continue;  // ill-conditioned basis: retry without P
-      // T = L^{-1} As L^{-T}
-      std::vector<double> T1((size_t)m * m), T((size_t)m * m);
-      for (int col = 0; col < m; ++col)  // solve L * T1(:,col) = As(:,col)
-        for (int i = 0; i < m; ++i) {
-          double v = As[(size_t)i * m + col];
-          for (int q = 0; q < i; ++q) v -= L[(size_t)i * m + q] * T1[(size_t)q * m + col];
-          T1[(size_t)i * m + col] = v / L[(size_t)i * m + i];
+      std::vector<double> lam, Q;
+      if (sym_eig(Gs, m, lam, Q) && lam[m - 1] > 0.0 && std::isfinite(lam[m - 1])) {
+        std::vector<int> keep;
+        for (int a = 0; a < m; ++a)
+          if (lam[a] > 1e-10 * lam[m - 1]) keep.push_back(a);
+        const int mk = (int)keep.size();
+        if (mk >= k) {
+          // Tm = Q(:, keep) * diag(lam_keep^-1/2)   (m x mk);  At = Tm' As Tm
+          std::vector<double> Tm((size_t)m * mk), AT((size_t)m * mk), At((size_t)mk * mk);
+          for (int a = 0; a < m; ++a)
+            for (int q = 0; q < mk; ++q) Tm[(size_t)a * mk + q] = Q[(size_t)a * m + keep[q]] / sqrt(lam[keep[q]]);
+          for (int a = 0; a < m; ++a)
+            for (int q = 0; q < mk; ++q) {
+              double s2 = 0.0;
+              for (int b = 0; b < m; ++b) s2 += As[(size_t)a * m + b] * Tm[(size_t)b * mk + q];
+              AT[(size_t)a * mk + q] = s2;
+            }
+          for (int r = 0; r < mk; ++r)
+            for (int q = 0; q < mk; ++q) {
+              double s2 = 0.0;
+              for (int a = 0; a < m; ++a) s2 += Tm[(size_t)a * mk + r] * AT[(size_t)a * mk + q];
+              At[(size_t)r * mk + q] = s2;
+            }
+          for (int r = 0; r < mk; ++r)
+            for (int q = r + 1; q < mk; ++q) {
+              const double v = 0.5 * (At[(size_t)r * mk + q] + At[(size_t)q * mk + r]);
+              At[(size_t)r * mk + q] = At[(size_t)q * mk + r] = v;
+            }
+          std::vector<double> ev, Zt;
+          bool okeig = sym_eig(At, mk, ev, Zt);
+          for (int c = 0; okeig && c < k; ++c) okeig = std::isfinite(ev[c]);
+          if (okeig) {
+            Cfull.assign((size_t)m * k, 0.0);
+            for (int a = 0; a < m; ++a)
+              for (int c = 0; c < k; ++c) {
+                double s2 = 0.0;
+                for (int q = 0; q < mk; ++q) s2 += Tm[(size_t)a * mk + q] * Zt[(size_t)q * mk + c];
+                Cfull[(size_t)a * k + c] = s2 * dscale[a];
+              }
+            ritz.assign(ev.begin(), ev.begin() + k);
+            idx = bidx;
+            solved = true;
+          }
         }
-      for (int row = 0; row < m; ++row)  // T(row,:) L' = T1(row,:)  <=> L T(row,:)' = T1(row,:)'
-        for (int i = 0; i < m; ++i) {
-          double v = T1[(size_t)row * m + i];
-          for (int q = 0; q < i; ++q) v -= L[(size_t)i * m + q] * T[(size_t)row * m + q];
-          T[(size_t)row * m + i] = v / L[(size_t)i * m + i];
-        }
-      for (int a = 0; a < m; ++a)
-        for (int b = a + 1; b < m; ++b) {
-          const double v = 0.5 * (T[(size_t)a * m + b] + T[(size_t)b * m + a]);
-          T[(size_t)a * m + b] = T[(size_t)b * m + a] = v;
-        }
-      std::vector<double> ev, Z;
-      if (!sym_eig(T, m, ev, Z)) continue;
-      // C = D * L^{-T} * Z(:, 0..k)
-      Cfull.assign((size_t)m * k, 0.0);
-      for (int c = 0; c < k; ++c) {
-        std::vector<double> x(m);
-        for (int i = m - 1; i >= 0; --i) {  // L' x = z
-          double v = Z[(size_t)i * m + c];
-          for (int q = i + 1; q < m; ++q) v -= L[(size_t)q * m + i] * x[q];
-          x[i] = v / L[(size_t)i * m + i];
-        }
-        for (int i = 0; i < m; ++i) Cfull[(size_t)i * k + c] = x[i] * dscale[i];
       }
-      ritz.assign(ev.begin(), ev.begin() + k);
-      idx = bidx;
-      solved = true;
     }
     if (!solved) {
       if (!haveW) return msdp_fail(h, MANISDP_E_NUMERIC, "lobpcg: starting block is rank deficient");
@@ -498,7 +522,10 @@ static int small_dense_eig(manisdp_handle* h, int delta, std::vector<double>& va
 // ---- KKT --------------------------------------------------------------------------------------------------------------
 struct EigStore {
   EigWork lo, hi;
-  bool warm_lo = false;
+  bool warm_lo = false, warm_hi = false;
+  int64_t rank_version = -1;
+  int rank_p = -1;
+  std::vector<double> rank_ev, rank_Z;
 };
 #include <map>
 #include <mutex>
@@ -549,13 +576,14 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
     std::vector<double> hv;
     double r2 = 0.0;
     int it2 = 0;
-    MSDP_TRY(lobpcg(h, st.hi, 1, 1, 0.0, 60, 0, hv, &r2, &it2));
+    MSDP_TRY(lobpcg(h, st.hi, 1, 1, 0.0, 1e-6, 80, st.warm_hi ? 1 : 0, hv, &r2, &it2));
+    st.warm_hi = true;
     lam_max = hv[0];
     const int k = 4 * ((delta + 4 + 3) / 4);
     const bool warm = st.warm_lo && st.lo.k == k;
     MSDP_TRY(eig_alloc(h, st.lo, k));
     const double tol_abs = eig_tol * (1.0 + fabs(lam_max));
-    MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_abs, 2000, warm ? 1 : 0, vals, &resid, &iters));
+    MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_abs, 0.0, 1500, warm ? 1 : 0, vals, &resid, &iters));
     st.warm_lo = true;
     // keep the wanted vectors for manisdp_escape
     const int kld = st.lo.kld;
@@ -653,14 +681,25 @@ static int install_combination(manisdp_handle* h, const std::vector<double>& Cm,
 
 int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, int64_t* pnew_out) {
   const int p = (int)h->p;
-  std::vector<double> G, ev, Z;
-  MSDP_TRY(gram_general(h, h->Ybuf[h->pt], (int)h->ld, p, h->Ybuf[h->pt], (int)h->ld, p, G));
-  for (int i = 0; i < p; ++i)
-    for (int j = i + 1; j < p; ++j) {
-      const double v = 0.5 * (G[(size_t)i * p + j] + G[(size_t)j * p + i]);
-      G[(size_t)i * p + j] = G[(size_t)j * p + i] = v;
-    }
-  if (!sym_eig(G, p, ev, Z)) return msdp_fail(h, MANISDP_E_NUMERIC, "rank_cut: eigen-decomposition failed");
+  // the drivers ask for the rank first and cut afterwards: keep the decomposition of the unchanged point
+  g_store_mu.lock();
+  EigStore& es = g_store[h];
+  g_store_mu.unlock();
+  if (es.rank_version != h->y_version || es.rank_p != p) {
+    std::vector<double> G;
+    MSDP_TRY(gram_general(h, h->Ybuf[h->pt], (int)h->ld, p, h->Ybuf[h->pt], (int)h->ld, p, G));
+    for (int i = 0; i < p; ++i)
+      for (int j = i + 1; j < p; ++j) {
+        const double v = 0.5 * (G[(size_t)i * p + j] + G[(size_t)j * p + i]);
+        G[(size_t)i * p + j] = G[(size_t)j * p + i] = v;
+      }
+    if (!sym_eig(G, p, es.rank_ev, es.rank_Z))
+      return msdp_fail(h, MANISDP_E_NUMERIC, "rank_cut: eigen-decomposition failed");
+    es.rank_version = h->y_version;
+    es.rank_p = p;
+  }
+  const std::vector<double>& ev = es.rank_ev;
+  const std::vector<double>& Z = es.rank_Z;
   // singular values of Y = sqrt(eigenvalues of Y'Y), descending (ManiSDP_unitdiag.m:72-74)
   const double s1 = sqrt(std::max(0.0, ev[p - 1]));
   int r = 0;
@@ -766,6 +805,7 @@ int msdp_line_search(manisdp_handle* h, double* alpha_out) {
   KERNEL_CHECK(h);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->pt ^= 1;
+  h->y_version++;
   h->cache_valid = h->grad_valid = 0;
   if (alpha_out) *alpha_out = alpha;
   return MANISDP_OK;

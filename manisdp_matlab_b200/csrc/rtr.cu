@@ -172,6 +172,7 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
   if (opt.Delta_bar <= 0) opt.Delta_bar = typicaldist;
   if (opt.Delta0 <= 0) opt.Delta0 = opt.Delta_bar / 8.0;
   const int use_graph = (opt.use_graph != 0) && (h->world <= 1);
+  h->y_version++;
 
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   TrSetup s{opt.Delta0, opt.Delta_bar, opt.rho_prime, opt.rho_regularization, opt.kappa, opt.theta,

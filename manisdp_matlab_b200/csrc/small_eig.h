@@ -14,7 +14,9 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
   w.assign(n, 0.0);
   std::vector<double> e(n, 0.0);
   if (n == 0) return true;
-  auto v = [&](int i, int j) -> double& { return V[(size_t)i * n + j]; };
+  // internal storage is COLUMN-major (A is symmetric, so V = A is valid either way): the hot loops of both phases
+  // run down columns (v(k, j) over k), which is then unit stride; the result is transposed once at the end
+  auto v = [&](int i, int j) -> double& { return V[(size_t)j * n + i]; };
   // --- Householder reduction to tridiagonal form, accumulating the transformation in V
   for (int j = 0; j < n; ++j) w[j] = v(n - 1, j);
   for (int i = n - 1; i > 0; --i) {
@@ -158,6 +160,8 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
       for (int j = 0; j < n; ++j) std::swap(v(j, i), v(j, k));
     }
   }
+  for (int i = 0; i < n; ++i)  // column-major -> row-major
+    for (int j = i + 1; j < n; ++j) std::swap(V[(size_t)i * n + j], V[(size_t)j * n + i]);
   return true;
 }
 
