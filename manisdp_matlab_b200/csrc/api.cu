@@ -287,6 +287,7 @@ static void free_all(manisdp_handle* h) {
     if (a) cudaFree(a);
   if (h->C.rowptr) cudaFree(h->C.rowptr);
   if (h->spmm_bptr) cudaFree(h->spmm_bptr);
+  if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->C.col) cudaFree(h->C.col);
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);

@@ -134,6 +134,9 @@ struct manisdp_handle {
   int64_t spmm_l2_target = 64ll << 20; // bytes of operand rows per column block
   int C_sorted = 0;                    // rows of C are column-sorted
   double C_far_fraction = 0.0;         // share of entries whose column is farther than an L2 window from the row
+  // split-K workspace of the DMMA GEMM (gemm_f64.cu)
+  double* gemm_ws = nullptr;
+  size_t gemm_ws_cap = 0;
   // NCCL
   void* nccl_comm = nullptr;
   std::string err;
