@@ -581,10 +581,10 @@ extern "C" int manisdp_line_search(manisdp_t* h, double* alpha) {
 // host-only diagnostic: the small dense symmetric eigensolver used by the eigen / rank steps (no GPU needed)
 #include "small_eig.h"
 extern "C" int manisdp_test_sym_eig(const double* A, int32_t n, double* w, double* V) {
-  if (!A || !w || !V || n < 0) return MANISDP_E_ARG;
+  if (!A || !w || n < 0) return MANISDP_E_ARG;
   std::vector<double> a(A, A + (size_t)n * n), ww, vv;
-  if (!sym_eig(a, n, ww, vv)) return MANISDP_E_NUMERIC;
+  if (!sym_eig(a, n, ww, vv, V != nullptr)) return MANISDP_E_NUMERIC;  // V == NULL: eigenvalues only
   for (int i = 0; i < n; ++i) w[i] = ww[i];
-  for (size_t i = 0; i < (size_t)n * n; ++i) V[i] = vv[i];
+  for (size_t i = 0; V && i < (size_t)n * n; ++i) V[i] = vv[i];
   return MANISDP_OK;
 }

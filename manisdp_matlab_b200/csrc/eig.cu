@@ -525,7 +525,8 @@ struct EigStore {
   bool warm_lo = false, warm_hi = false;
   int64_t rank_version = -1;
   int rank_p = -1;
-  std::vector<double> rank_ev, rank_Z;
+  std::vector<double> rank_ev, rank_Z, rank_G;
+  bool rank_have_Z = false;
 };
 #include <map>
 #include <mutex>
@@ -686,19 +687,35 @@ int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, in
   EigStore& es = g_store[h];
   g_store_mu.unlock();
   if (es.rank_version != h->y_version || es.rank_p != p) {
-    std::vector<double> G;
+    std::vector<double>& G = es.rank_G;
     MSDP_TRY(gram_general(h, h->Ybuf[h->pt], (int)h->ld, p, h->Ybuf[h->pt], (int)h->ld, p, G));
     for (int i = 0; i < p; ++i)
       for (int j = i + 1; j < p; ++j) {
         const double v = 0.5 * (G[(size_t)i * p + j] + G[(size_t)j * p + i]);
         G[(size_t)i * p + j] = G[(size_t)j * p + i] = v;
       }
-    if (!sym_eig(G, p, es.rank_ev, es.rank_Z))
+    // the rank estimate needs the singular values only; eigenvectors are computed when a cut is actually applied
+    std::vector<double> scratch;
+    if (!sym_eig(G, p, es.rank_ev, scratch, false))
       return msdp_fail(h, MANISDP_E_NUMERIC, "rank_cut: eigen-decomposition failed");
+    es.rank_have_Z = false;
     es.rank_version = h->y_version;
     es.rank_p = p;
   }
   const std::vector<double>& ev = es.rank_ev;
+  {
+    const double s1t = sqrt(std::max(0.0, ev[p - 1]));
+    int rt = 0;
+    for (int i = 0; i < p; ++i)
+      if (sqrt(std::max(0.0, ev[i])) >= theta * s1t) ++rt;
+    if (apply && rt <= p - 1 && rt >= 1 && !es.rank_have_Z) {
+      std::vector<double> ev2;
+      if (!sym_eig(es.rank_G, p, ev2, es.rank_Z, true))
+        return msdp_fail(h, MANISDP_E_NUMERIC, "rank_cut: eigen-decomposition failed");
+      es.rank_ev = ev2;
+      es.rank_have_Z = true;
+    }
+  }
   const std::vector<double>& Z = es.rank_Z;
   // singular values of Y = sqrt(eigenvalues of Y'Y), descending (ManiSDP_unitdiag.m:72-74)
   const double s1 = sqrt(std::max(0.0, ev[p - 1]));

@@ -9,7 +9,10 @@
 
 // A: n x n symmetric, row-major.  On return V (n x n, row-major) holds eigenvectors in COLUMNS and w the eigenvalues in
 // ascending order.  Returns false if QL fails to converge (never observed; 60 sweeps per eigenvalue allowed).
-inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& V) {
+// want_vectors = false: eigenvalues only (skips the accumulation of the Householder reflectors and the rotation
+// updates, ~5x cheaper); V is then scratch.
+inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& V,
+                    bool want_vectors = true) {
   V = A;
   w.assign(n, 0.0);
   std::vector<double> e(n, 0.0);
@@ -69,7 +72,8 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
     w[i] = hh;
   }
   for (int i = 0; i < n - 1; ++i) {
-    v(n - 1, i) = v(i, i);
+    v(n - 1, i) = v(i, i);  // the diagonal of the tridiagonal matrix is parked in the last row
+    if (!want_vectors) continue;
     v(i, i) = 1.0;
     const double hh = w[i + 1];
     if (hh != 0.0) {
@@ -131,7 +135,7 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
           c = p / r;
           p = c * w[i] - s * g;
           w[i + 1] = h + s * (c * g + s * w[i]);
-          for (int k = 0; k < n; ++k) {
+          for (int k = 0; want_vectors && k < n; ++k) {
             h = v(k, i + 1);
             v(k, i + 1) = s * v(k, i) + c * h;
             v(k, i) = c * v(k, i) - s * h;

@@ -61,3 +61,33 @@ def synthetic_torus(side, seed=0):
     ej = np.concatenate([right, down])
     w = rng.choice([-1.0, 1.0], size=len(ei))
     return n, ei, ej, w
+
+
+def read_sdpa(path):
+    """SDPA sparse format (.dat-s, SDPLIB) -> SeDuMi (At, b, c, K) for a single semidefinite block, with the sign
+    convention of the reference's reader (src/basicfunction/fromsdpa.m:95,127,141): SDPA's dual
+    max <F0,Y> s.t. <Fi,Y> = c_i becomes  min <-F0, X>  s.t. <Fi, X> = c_i,  so  obj = -(SDPLIB optimal value).
+    Entries are given for the upper triangle and mirrored; row index of At / c is the column-major j*n + i."""
+    with open(path) as fh:
+        lines = [ln for ln in fh if ln.strip() and ln.lstrip()[0] not in '"*']
+    clean = lambda s: s.translate(str.maketrans("{}(),", "     "))
+    m = int(clean(lines[0]).split()[0])
+    nblocks = int(clean(lines[1]).split()[0])
+    dims = [int(t) for t in clean(lines[2]).split()[:nblocks]]
+    if nblocks != 1 or dims[0] <= 0:
+        raise ValueError("read_sdpa: only one semidefinite block is supported (K.s scalar, as the four primal drivers)")
+    n = dims[0]
+    b = np.array([float(t) for t in clean(lines[3]).split()[:m]])
+    E = np.array([[float(t) for t in ln.split()[:5]] for ln in lines[4:]])
+    mat = E[:, 0].astype(np.int64)
+    i = E[:, 2].astype(np.int64) - 1
+    j = E[:, 3].astype(np.int64) - 1
+    v = E[:, 4]
+    off = i != j
+    rows = np.concatenate([j * n + i, (i * n + j)[off]])
+    cols = np.concatenate([mat, mat[off]])
+    vals = np.concatenate([v, v[off]])
+    obj = cols == 0
+    c = -sp.csc_matrix((vals[obj], (rows[obj], np.zeros(obj.sum(), dtype=np.int64))), shape=(n * n, 1))
+    At = sp.csc_matrix((vals[~obj], (rows[~obj], cols[~obj] - 1)), shape=(n * n, m))
+    return At, b, c, {"s": n}

@@ -70,3 +70,6 @@ def test_host_small_eigensolver(engine_lib):
         assert np.allclose(w, np.linalg.eigvalsh(A), atol=1e-11 * max(1, n))
         assert np.abs(A @ V - V * w).max() < 1e-11 * max(1, n)
         assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12 * max(1, n)
+        w2 = np.empty(n)  # eigenvalues-only path (rank step): V = NULL
+        assert engine_lib.manisdp_test_sym_eig(_lib._pf(np.ascontiguousarray(A)), n, _lib._pf(w2), None) == 0
+        assert np.allclose(w2, np.linalg.eigvalsh(A), atol=1e-11 * max(1, n))
