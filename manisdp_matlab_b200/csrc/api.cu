@@ -327,8 +327,7 @@ const char* manisdp_last_error(const manisdp_t* h) { return h ? h->err.c_str() :
 int manisdp_set_Y(manisdp_t* h, const double* Y, int64_t p, int32_t layout) {
   if (!h || !Y) return msdp_fail(h, MANISDP_E_ARG, "null argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  // a new factor width makes the old point meaningless: drop it before resizing
-  h->p = 0;
+  // same width: the captured trust-region graphs stay valid (msdp_resize only invalidates them when p changes)
   MSDP_TRY(msdp_resize(h, p));
   return upload_rows(h, h->Ybuf[h->pt], Y, layout);
 }
@@ -349,7 +348,6 @@ int manisdp_get_p(manisdp_t* h, int64_t* p) {
 int manisdp_rand_Y(manisdp_t* h, int64_t p, uint64_t seed) {
   if (!h) return MANISDP_E_ARG;
   CUDA_TRY(h, cudaSetDevice(h->device));
-  h->p = 0;
   MSDP_TRY(msdp_resize(h, p));
   double* raw = h->Ybuf[h->pt ^ 1];
   k_randn_rows<<<grid_for(h, h->nloc * h->ld), MSDP_THREADS, 0, h->stream>>>(raw, h->nloc, h->p, h->ld,

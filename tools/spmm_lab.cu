@@ -170,6 +170,87 @@ float run_v2(const int* rowptr, const int* col, const double* val, const double*
   float ms; cudaEventElapsedTime(&ms, a, b); return ms / reps;
 }
 
+
+// V3: row-stationary sweep.  A CTA keeps the accumulator rows of a tile (WARPS*RPW rows x 64 doubles) in shared
+// memory and walks the B column blocks; all CTAs of a wave are in the same block at about the same time, so the operand
+// block (n/B rows) stays L2-resident while it is used and no partial rows go back to DRAM.
+template <int WARPS, int RPW, int UNR>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_v3(const int* __restrict__ bptr, const int* __restrict__ col,
+                                                      const double* __restrict__ val, const double* __restrict__ U,
+                                                      double* __restrict__ out, long n, int B) {
+  extern __shared__ __align__(16) double accs[];  // WARPS*RPW x LD
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int TR = WARPS * RPW;
+  double* myacc = accs + (size_t)wid * RPW * LD;
+  for (long tile = blockIdx.x; tile * TR < n; tile += gridDim.x) {
+    const long rowbase = tile * TR + (long)wid * RPW;
+    for (int i = lane; i < RPW * LD / 2; i += 32) reinterpret_cast<double2*>(myacc)[i] = make_double2(0, 0);
+    __syncwarp();
+    for (int b = 0; b < B; ++b) {
+      int e0 = 0, e1 = 0;
+      if (lane < RPW && rowbase + lane < n) {
+        e0 = __ldg(bptr + (size_t)b * n + rowbase + lane);
+        e1 = __ldg(bptr + (size_t)(b + 1) * n + rowbase + lane);
+      }
+      // software pipeline over the warp's rows: entries of row r+1 are loaded while row r gathers
+      int cn = 0; double wn = 0;
+      {
+        const int f0 = __shfl_sync(0xffffffffu, e0, 0), f1 = __shfl_sync(0xffffffffu, e1, 0);
+        if (f0 + lane < f1) { cn = __ldcs(col + f0 + lane); wn = __ldcs(val + f0 + lane); }
+      }
+      for (int r = 0; r < RPW; ++r) {
+        const int r0 = __shfl_sync(0xffffffffu, e0, r), r1 = __shfl_sync(0xffffffffu, e1, r);
+        int c = cn; double w = wn;
+        if (r + 1 < RPW) {
+          const int f0 = __shfl_sync(0xffffffffu, e0, r + 1), f1 = __shfl_sync(0xffffffffu, e1, r + 1);
+          cn = 0; wn = 0;
+          if (f0 + lane < f1) { cn = __ldcs(col + f0 + lane); wn = __ldcs(val + f0 + lane); }
+        }
+        if (r1 <= r0) continue;
+        double2 acc = reinterpret_cast<double2*>(myacc + (size_t)r * LD)[lane];
+        for (int base = r0; base < r1; base += 32) {
+          if (base > r0) { c = 0; w = 0; if (base + lane < r1) { c = __ldcs(col + base + lane); w = __ldcs(val + base + lane); } }
+          const int cnt = min(32, r1 - base);
+          for (int k = 0; k < cnt; k += UNR) {
+            double2 u[UNR]; double ww[UNR];
+#pragma unroll
+            for (int s = 0; s < UNR; ++s) {
+              if (k + s < cnt) {
+                const int cj = __shfl_sync(0xffffffffu, c, k + s);
+                ww[s] = __shfl_sync(0xffffffffu, w, k + s);
+                u[s] = __ldg(reinterpret_cast<const double2*>(U + (size_t)cj * LD) + lane);
+              } else { ww[s] = 0; u[s] = make_double2(0, 0); }
+            }
+#pragma unroll
+            for (int s = 0; s < UNR; ++s) { acc.x = fma(ww[s], u[s].x, acc.x); acc.y = fma(ww[s], u[s].y, acc.y); }
+          }
+        }
+        reinterpret_cast<double2*>(myacc + (size_t)r * LD)[lane] = acc;
+      }
+    }
+    __syncwarp();
+    for (int r = 0; r < RPW; ++r)
+      if (rowbase + r < n) __stcs(reinterpret_cast<double2*>(out + (size_t)(rowbase + r) * LD) + lane,
+                                  reinterpret_cast<double2*>(myacc + (size_t)r * LD)[lane]);
+    __syncwarp();
+  }
+}
+
+template <int WARPS, int RPW, int UNR>
+float run_v3(const int* rowptr, const int* col, const double* val, const double* U, double* out, long n, int B, int* bptr,
+             int reps) {
+  const size_t smem = (size_t)WARPS * RPW * LD * 8;
+  CK(cudaFuncSetAttribute(k_v3<WARPS, RPW, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_block_ptrs<<<1184, 256>>>(rowptr, col, n, (n + B - 1) / B, B, bptr);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  k_v3<WARPS, RPW, UNR><<<148, WARPS * 32, smem>>>(bptr, col, val, U, out, n, B);
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(a);
+  for (int r = 0; r < reps; ++r) k_v3<WARPS, RPW, UNR><<<148, WARPS * 32, smem>>>(bptr, col, val, U, out, n, B);
+  cudaEventRecord(b); CK(cudaEventSynchronize(b));
+  float ms; cudaEventElapsedTime(&ms, a, b); return ms / reps;
+}
+
 int main(int argc, char** argv) {
   const long n = argc > 1 ? atol(argv[1]) : 1000000; const int deg = 48;
   std::vector<int> rp(n + 1), ci((size_t)n * deg); std::vector<double> va((size_t)n * deg);
@@ -207,6 +288,15 @@ int main(int argc, char** argv) {
     printf("{\"variant\": \"%s\", \"passes\": %d, \"blocks_per_sm\": %d, \"ms\": %.3f, \"maxdiff\": %.2e}\n", name, B, bps, ms, md);
     fflush(stdout);
   };
+  if (argc > 2) {  // row-stationary sweep only
+    for (int B : {1, 4, 8, 12, 16}) {
+      check("v3_rs_w16_r24_u8", B, 1, run_v3<16, 24, 8>(drp, dci, dva, U, o1, n, B, bptr, 5));
+      check("v3_rs_w32_r12_u8", B, 1, run_v3<32, 12, 8>(drp, dci, dva, U, o1, n, B, bptr, 5));
+      check("v3_rs_w32_r12_u4", B, 1, run_v3<32, 12, 4>(drp, dci, dva, U, o1, n, B, bptr, 5));
+      check("v3_rs_w24_r16_u8", B, 1, run_v3<24, 16, 8>(drp, dci, dva, U, o1, n, B, bptr, 5));
+    }
+    return 0;
+  }
   for (int B : {1, 4, 6, 8, 12}) {
     check("v2_bulk_w8_s8", B, 3, run_v2<8, 8>(drp, dci, dva, U, o1, n, B, bptr, 3, 5));
     check("v2_bulk_w8_s8", B, 5, run_v2<8, 8>(drp, dci, dva, U, o1, n, B, bptr, 5, 5));
