@@ -370,7 +370,26 @@ def time_to_kkt():
         out["cpu_port_hv"] = int(dc["hv_count"])
     except Exception as e:  # the checker is optional here
         out["cpu_port_error"] = str(e)
-    return out
+    return [out, time_to_kkt_bqp60()]
+
+
+def time_to_kkt_bqp60():
+    """BASELINE config 2: BQP q = 60 (n = 1831, m = 1 155 281) through the drop-in ManiSDP_unitdiag, tol 1e-8."""
+    from manisdp_matlab_b200 import ManiSDP_unitdiag, problems as P
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bqp_60_1.npz"))
+    t0 = time.perf_counter()
+    At, b, c, K = P.bqpmom(60, d["Q"], d["e"])
+    c = c / np.abs(c).max()  # example/example_bqp.m:31-41
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    X, obj, data = ManiSDP_unitdiag(At, b, c, K, dict(tol=1e-8, verbose=False))
+    dt = time.perf_counter() - t0
+    return {"instance": "BQP q=60 (bqp_Q_60_1 / bqp_e_60_1), ManiSDP_unitdiag", "n": int(K["s"]), "m": int(At.shape[1]),
+            "seconds": dt, "obj": obj, "eta": max(data["gap"], data["pinf"], data["dinf"]), "iters": int(data["iters"]),
+            "hv": int(data["hv_count"]), "tr_seconds": data["tr_seconds"],
+            "hv_per_s": data["hv_count"] / max(data["tr_seconds"], 1e-9), "status": data["status"],
+            "generate_seconds": t_gen, "known_optimum": -201.01858191,
+            "cpu_port_seconds_build_container": 353.0}
 
 
 def main():
