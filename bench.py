@@ -301,6 +301,15 @@ def run_ours(args, rank, world):
                 "traffic": args.traffic, "algorithmic_bytes_per_launch": st.bytes_per_hv,
                 "ms_per_launch": ms, "gflops": st.flops_per_hv / (ms * 1e-3) / 1e9,
                 "includes_allgather": world > 1}
+    # the fused vector kernels of the loop (K5-K7), same roofline arithmetic
+    vec = None
+    if world == 1:
+        vec = {}
+        for which, nm in enumerate(["k_retract (24np B)", "k_project (24np B)", "k_tcg_update (56np B)",
+                                    "k_tcg_dir (32np B)"]):
+            vms, vbytes = h.vec_bench(which, 20)
+            vec[nm] = {"ms_per_launch": vms, "achieved_GBps": vbytes / (vms * 1e-3) / 1e9,
+                       "frac": vbytes / (vms * 1e-3) / 1e9 / peak}
     h.close()
     secondary = None
     if world == 1 and args.workload == "er" and not args.no_secondary:
@@ -327,7 +336,8 @@ def run_ours(args, rank, world):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(Y0.nbytes),
                     "d2h_bytes_per_step": int(out_host.nbytes) + 256, "steps": ne},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "setup_s": {"generate": t_gen, "create": t_create}, "kkt": kkt, "secondary": secondary}
+            "setup_s": {"generate": t_gen, "create": t_create}, "kkt": kkt, "secondary": secondary,
+            "vector_kernels": vec}
     print(json.dumps(line), flush=True)
 
 

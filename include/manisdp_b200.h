@@ -172,6 +172,9 @@ int manisdp_grad(manisdp_t *h, double *gradnorm);
 int manisdp_hess(manisdp_t *h);
 /* benchmark hook: `reps` back-to-back Hessian products SLOT_U -> SLOT_H; returns mean device ms per product */
 int manisdp_hess_bench(manisdp_t *h, int32_t reps, double *ms_per_hv);
+/* benchmark hook for the fused vector kernels: which = 0 retraction, 1 tangent projection, 2 tCG update pass,
+ * 3 tCG direction pass; returns mean device ms per launch and the algorithmic bytes of one launch */
+int manisdp_vec_bench(manisdp_t *h, int32_t which, int32_t reps, double *ms_per_launch, double *bytes);
 /* manifold ops on slots: dst = retr(Y, eta) ; dst = proj_Y(src) */
 int manisdp_retract(manisdp_t *h, int32_t eta_slot, int32_t dst_slot);
 int manisdp_project(manisdp_t *h, int32_t src_slot, int32_t dst_slot);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "manisdp_grad": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "manisdp_hess": (C.c_int, [_H]),
     "manisdp_hess_bench": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_double)]),
+    "manisdp_vec_bench": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "manisdp_retract": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "manisdp_project": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "manisdp_tr_solve": (C.c_int, [_H, C.POINTER(TrOptions), C.POINTER(TrInfo)]),
@@ -290,6 +291,12 @@ class Handle:
         ms = C.c_double()
         self._ck(self.lib.manisdp_hess_bench(self._h, reps, C.byref(ms)), "hess_bench")
         return ms.value
+
+    def vec_bench(self, which, reps=20):
+        """(ms per launch, algorithmic bytes) of a fused vector kernel: 0 retract, 1 project, 2 tCG update, 3 tCG dir"""
+        ms, nb = C.c_double(), C.c_double()
+        self._ck(self.lib.manisdp_vec_bench(self._h, which, reps, C.byref(ms), C.byref(nb)), "vec_bench")
+        return ms.value, nb.value
 
     def retract(self, eta):
         self.slot_set(SLOT_U, eta)

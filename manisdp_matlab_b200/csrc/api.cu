@@ -586,3 +586,53 @@ extern "C" int manisdp_test_sym_eig(const double* A, int32_t n, double* w, doubl
   for (size_t i = 0; V && i < (size_t)n * n; ++i) V[i] = vv[i];
   return MANISDP_OK;
 }
+
+// benchmark hook for the fused vector kernels (K5-K7): `reps` back-to-back launches timed with CUDA events.
+//   which: 0 retract (24 np bytes), 1 tangent projection (24 np), 2 tCG update pass (56 np), 3 tCG direction pass (32 np)
+// The tCG passes run on the solver's own workspace with a benign scalar state (alpha = beta = 1e-3, not stopped); the
+// workspace is re-initialised by the next tr_solve.
+__global__ void k_bench_state(RtrState* st) {
+  st->stop = 0;
+  st->branch = 0;
+  st->alpha = 1e-3;
+  st->beta = 1e-3;
+  st->tau = 0.0;
+  st->j = 0;
+  st->maxinner = 1 << 30;
+  st->mininner = 1 << 30;  // never satisfies the residual stop, so `stop` stays 0 across the repetitions
+  st->model_value = 1e300;
+  st->kappa = 0.1;
+  st->theta = 1.0;
+  st->norm_r0 = 1.0;
+  st->z_r = 1.0;
+  st->ticket = 0u;
+}
+extern "C" int manisdp_vec_bench(manisdp_t* h, int32_t which, int32_t reps, double* ms_per_launch, double* bytes) {
+  if (!h || h->p <= 0 || reps < 1 || which < 0 || which > 3)
+    return msdp_fail(h, MANISDP_E_ARG, "vec_bench: bad argument / no factor set");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const double np8 = 8.0 * (double)h->nloc * (double)h->ld;
+  const double mult[4] = {3.0, 3.0, 7.0, 4.0};
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0 = warm-up
+    k_bench_state<<<1, 1, 0, h->stream>>>(h->st);
+    KERNEL_CHECK(h);
+    if (pass == 1) CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    const int n_it = pass == 0 ? 2 : reps;
+    for (int i = 0; i < n_it; ++i) {
+      switch (which) {
+        case 0: MSDP_TRY(msdp_launch_retract(h, h->Ybuf[h->pt], h->Uslot, h->Hslot, 0)); break;
+        case 1: MSDP_TRY(msdp_launch_project(h, h->Ybuf[h->pt], h->Uslot, h->Hslot)); break;
+        case 2: MSDP_TRY(msdp_launch_tcg_update(h, 0, 0, 1)); break;  // defer = 1: totals land in st->tmp only
+        default: MSDP_TRY(msdp_launch_tcg_dir(h)); break;
+      }
+    }
+    if (pass == 1) CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  }
+  CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (ms_per_launch) *ms_per_launch = (double)ms / reps;
+  if (bytes) *bytes = mult[which] * np8;
+  h->cache_valid = h->grad_valid = 0;
+  return MANISDP_OK;
+}
