@@ -227,3 +227,4 @@ def ManiSDP_unittrace(At, b, c, K, options=None):
 def ManiSDP(At, b, c, K, options=None):
     """src/primal/ManiSDP.m:6"""
     return _affine_driver("general", At, b, c, K, options)
+

@@ -27,3 +27,41 @@ def test_bqpmom_sizes_match_reference_log():
         Q = rng.standard_normal((q, q))
         At, b, c, K = P.bqpmom(q, Q + Q.T, rng.standard_normal(q))
         assert (K["s"], At.shape[1]) == (n, m)
+
+
+def test_embed_blocks_against_reference_single_block_form():
+    """multi-block -> single-block index embedding (groundwork for SURVEY 8f rank 3).  data/SDP_demo_1.mat carries the
+    authors' own single-block version of the same SDP (sedumi.At_full / c_full): every embedded column must appear
+    there, in order, and c must match exactly."""
+    import scipy.sparse as sp
+    from manisdp_matlab_b200 import problems as P
+    d = np.load(os.path.join(GOLDEN, "sdp_demo_1.npz"))
+    At = sp.csc_matrix((d["At_data"], d["At_indices"], d["At_indptr"]), shape=tuple(d["At_shape"]))
+    c = sp.csc_matrix((d["c_val"], (d["c_idx"], np.zeros(len(d["c_idx"]), dtype=int))), shape=(At.shape[0], 1))
+    ns = d["ns"]
+    Ab, bb, cb, N, off = P.embed_blocks(At, c, {"s": ns}, d["b"])
+    assert N == ns.sum() == 2240 and Ab.shape == (N * N, At.shape[1]) and Ab.nnz == At.nnz
+    # support is block diagonal and symmetric
+    coo = Ab.tocoo()
+    i, j = coo.row % N, coo.row // N
+    bi = np.searchsorted(off, i, side="right") - 1
+    bj = np.searchsorted(off, j, side="right") - 1
+    assert np.array_equal(bi, bj)
+    ref = "/root/reference/data/SDP_demo_1.mat"
+    if os.path.exists(ref):
+        import scipy.io as sio
+        sed = sio.loadmat(ref, squeeze_me=True, struct_as_record=False)["SDP_1"].sedumi
+        Af = sp.csc_matrix(sed.At_full)
+        Af.sort_indices()
+        Ab.sort_indices()
+        assert (sp.csc_matrix(sed.c_full).reshape(-1, 1) != cb).nnz == 0
+
+        def key(M, k):
+            s, e = M.indptr[k], M.indptr[k + 1]
+            return (M.indices[s:e].tobytes(), np.round(M.data[s:e], 12).tobytes())
+
+        where = {}
+        for k in range(Af.shape[1]):
+            where.setdefault(key(Af, k), k)
+        pos = [where.get(key(Ab, k), -1) for k in range(Ab.shape[1])]
+        assert min(pos) >= 0 and all(a < b for a, b in zip(pos, pos[1:]))
