@@ -12,6 +12,13 @@
 #include "rowops.cuh"
 #include "small_eig.h"
 
+#include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
+// coarse accounting of the eigen step (MANISDP_EIG_DEBUG=1 prints it at destroy): device wait vs host Rayleigh-Ritz
+static double g_eig_wait_s = 0.0, g_eig_host_s = 0.0;
+static long g_eig_iters_total = 0;
+
 #define EIG_TR 32       // rows per shared-memory tile
 #define EIG_MAXNB 48    // 3 * block size
 
@@ -342,7 +349,15 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
     KERNEL_CHECK(h);
     if (h->world > 1) MSDP_TRY(msdp_dist_allreduce_buf(h, w.gout, 2 * nent + kld));
     CUDA_TRY(h, cudaMemcpyAsync(w.hbuf, w.gout, ((size_t)2 * nent + kld) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    const auto t_wait0 = std::chrono::steady_clock::now();
     CUDA_TRY(h, cudaStreamSynchronize(s));
+    const auto t_host0 = std::chrono::steady_clock::now();
+    g_eig_wait_s += std::chrono::duration<double>(t_host0 - t_wait0).count();
+    struct HostTimer {
+      std::chrono::steady_clock::time_point t0;
+      ~HostTimer() { g_eig_host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+    } host_timer{t_host0};
+    g_eig_iters_total += 1;
     const double* hG = w.hbuf;
     const double* hGA = w.hbuf + nent;
     if (haveW) {
@@ -534,6 +549,9 @@ static std::map<manisdp_handle*, EigStore> g_store;
 static std::mutex g_store_mu;
 void msdp_eig_release(manisdp_handle* h) {
   std::lock_guard<std::mutex> lk(g_store_mu);
+  if (getenv("MANISDP_EIG_DEBUG") && g_eig_iters_total > 0)
+    fprintf(stderr, "[manisdp eig] iterations %ld, device wait %.3f s, host part (RR + launches) %.3f s\n",
+            g_eig_iters_total, g_eig_wait_s, g_eig_host_s);
   auto it = g_store.find(h);
   if (it != g_store.end()) {
     eig_free(it->second.lo);

@@ -179,14 +179,18 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
             opt.maxinner, opt.mininner};
   k_tr_setup<<<1, 1, 0, h->stream>>>(h->st, s);
   KERNEL_CHECK(h);
-  // getCostGrad at the initial point (trustregions.m:405)
-  if (h->world > 1) {
-    MSDP_TRY(msdp_dist_allgather_rows(h, h->Ybuf[h->pt], h->gatherbuf));
-    MSDP_TRY(msdp_costgrad(h, -2, CG_TR_DEFER));
-    MSDP_TRY(msdp_dist_allreduce_tmp(h, 2));
-    MSDP_TRY(msdp_dist_finish_init(h));
-  } else {
-    MSDP_TRY(msdp_costgrad(h, -2, CG_INIT));
+  // getCostGrad at the initial point (trustregions.m:405).  When the point has not changed since the last closure
+  // call -- e.g. consecutive tr_solve calls, or tr_solve right after manisdp_cost -- the device already holds f, the
+  // gradient and the per-point caches (the equivalent of Manopt's StoreDB hit, getCost.m:42-55), so nothing is redone.
+  if (!(h->cache_valid && h->grad_valid)) {
+    if (h->world > 1) {
+      MSDP_TRY(msdp_dist_allgather_rows(h, h->Ybuf[h->pt], h->gatherbuf));
+      MSDP_TRY(msdp_costgrad(h, -2, CG_TR_DEFER));
+      MSDP_TRY(msdp_dist_allreduce_tmp(h, 2));
+      MSDP_TRY(msdp_dist_finish_init(h));
+    } else {
+      MSDP_TRY(msdp_costgrad(h, -2, CG_INIT));
+    }
   }
   MSDP_TRY(msdp_sync_state(h));
   h->cache_valid = 1;
@@ -227,7 +231,11 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
     } else {
       MSDP_TRY(msdp_launch_tcg_init(h));
       int done = 0, issued = 0;
-      int chunk = 4;
+      // Iterations queued after tCG has stopped are no-ops for the kernels but NOT for the NCCL exchanges of a
+      // row-sharded handle (an all-gather of the factor each), so those are issued one at a time: a 20 us flag read
+      // per iteration against a >= 1 ms exchange.  Single-GPU stream mode grows the chunk instead.
+      const int chunk_cap = (h->world > 1) ? 1 : 32;
+      int chunk = (h->world > 1) ? 1 : 4;
       while (!done && issued < opt.maxinner) {
         int c = chunk;
         if (c > opt.maxinner - issued) c = opt.maxinner - issued;
@@ -237,7 +245,7 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
                                     h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         done = (h->st_host->stop != 0);
-        if (chunk < 32) chunk *= 2;
+        if (chunk < chunk_cap) chunk *= 2;
       }
       MSDP_TRY(tr_tail(h));
     }
