@@ -288,6 +288,7 @@ static void free_all(manisdp_handle* h) {
   if (h->C.rowptr) cudaFree(h->C.rowptr);
   if (h->spmm_bptr) cudaFree(h->spmm_bptr);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
+  if (h->owner_bptr) cudaFree(h->owner_bptr);
   if (h->C.col) cudaFree(h->C.col);
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);
@@ -444,8 +445,12 @@ int manisdp_hess(manisdp_t* h) {
   if (!h || h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "hess: no factor set");
   CUDA_TRY(h, cudaSetDevice(h->device));
   MSDP_TRY(msdp_ensure_costgrad(h));
-  if (h->world > 1) MSDP_TRY(msdp_dist_allgather_rows(h, h->Uslot, h->gatherbuf));
-  MSDP_TRY(msdp_hess_dir(h, h->Uslot, h->Hslot, TAIL_NONE));
+  if (msdp_pipeline_ok(h)) {
+    MSDP_TRY(msdp_maxcut_hess_pipelined(h, h->Uslot, h->Hslot, 0, TAIL_NONE));
+  } else {
+    if (h->world > 1) MSDP_TRY(msdp_dist_allgather_rows(h, h->Uslot, h->gatherbuf));
+    MSDP_TRY(msdp_hess_dir(h, h->Uslot, h->Hslot, TAIL_NONE));
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->hv_total += 1;
   return MANISDP_OK;
@@ -457,8 +462,12 @@ int manisdp_hess_bench(manisdp_t* h, int32_t reps, double* ms_per_hv) {
   MSDP_TRY(msdp_ensure_costgrad(h));
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < reps; ++i) {
-    if (h->world > 1) MSDP_TRY(msdp_dist_allgather_rows(h, h->Uslot, h->gatherbuf));
-    MSDP_TRY(msdp_hess_dir(h, h->Uslot, h->Hslot, TAIL_NONE));
+    if (msdp_pipeline_ok(h)) {
+      MSDP_TRY(msdp_maxcut_hess_pipelined(h, h->Uslot, h->Hslot, 0, TAIL_NONE));
+    } else {
+      if (h->world > 1) MSDP_TRY(msdp_dist_allgather_rows(h, h->Uslot, h->gatherbuf));
+      MSDP_TRY(msdp_hess_dir(h, h->Uslot, h->Hslot, TAIL_NONE));
+    }
   }
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(h, cudaEventSynchronize(h->ev1));

@@ -139,6 +139,13 @@ struct manisdp_handle {
   size_t gemm_ws_cap = 0;
   // NCCL
   void* nccl_comm = nullptr;
+  // pipelined exchange (dist.cu / spmm.cu): second communicator + stream, one event per stage, owner-chunk pass pointers
+  void* nccl_comm2 = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr;
+  std::vector<cudaEvent_t> ev_stage;
+  int pipeline = 0;
+  int* owner_bptr = nullptr;
   std::string err;
 };
 

@@ -4,6 +4,7 @@
 // share it -- linking the system copy (2.27.3) into the process first breaks torch's own symbol resolution.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 #include "dist.h"
 #include "kernels.cuh"
@@ -17,6 +18,12 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  // optional (pipelined exchange): a second communicator + point-to-point stages
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)(void) = nullptr;
+  ncclResult_t (*GroupEnd)(void) = nullptr;
   bool ok = false;
 };
 NcclApi g_nccl;
@@ -45,6 +52,11 @@ bool nccl_load(std::string& why) {
   SYM(AllReduce, "ncclAllReduce")
   SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
+  *(void**)(&g_nccl.CommSplit) = dlsym(g_nccl.lib, "ncclCommSplit");
+  *(void**)(&g_nccl.Send) = dlsym(g_nccl.lib, "ncclSend");
+  *(void**)(&g_nccl.Recv) = dlsym(g_nccl.lib, "ncclRecv");
+  *(void**)(&g_nccl.GroupStart) = dlsym(g_nccl.lib, "ncclGroupStart");
+  *(void**)(&g_nccl.GroupEnd) = dlsym(g_nccl.lib, "ncclGroupEnd");
   g_nccl.ok = true;
   return true;
 }
@@ -68,12 +80,64 @@ int msdp_dist_init(manisdp_handle* h, const void* unique_id) {
   ncclComm_t comm;
   NCCL_TRY(h, g_nccl.CommInitRank(&comm, h->world, id, h->rank));
   h->nccl_comm = (void*)comm;
+  // Pipelined exchange (see msdp_dist_exchange_begin): its point-to-point stages run on their own stream and their own
+  // communicator, so they can overlap the scalar all-reduces and the product passes of the main stream.
+  // Measured on B200 x2 / x8 (profiles/r1_pipelined_exchange.txt): correct, but NCCL's point-to-point stages move a
+  // 64 MB chunk far slower than its all-gather moves the whole factor (5.98 ms vs 1.25 ms per product at N = 8; 2.58 vs
+  // 2.40 ms at N = 2), so the staged path is opt-in (MANISDP_PIPELINE=1) until the stages are peer copies of our own.
+  const char* ep = getenv("MANISDP_PIPELINE");
+  const int want = ep ? atoi(ep) : 0;
+  if (want && g_nccl.CommSplit && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd) {
+    ncclComm_t comm2 = nullptr;
+    if (g_nccl.CommSplit(comm, 0, h->rank, &comm2, nullptr) == ncclSuccess && comm2) {
+      h->nccl_comm2 = (void*)comm2;
+      CUDA_TRY(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+      h->ev_stage.resize((size_t)h->world);
+      for (auto& e : h->ev_stage) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->pipeline = 1;
+    }
+  }
   return MANISDP_OK;
 }
 
 void msdp_dist_destroy(manisdp_handle* h) {
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  if (h->nccl_comm2 && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm2);
   if (h->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
-  h->nccl_comm = nullptr;
+  h->nccl_comm = h->nccl_comm2 = nullptr;
+  for (auto& e : h->ev_stage)
+    if (e) cudaEventDestroy(e);
+  h->ev_stage.clear();
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  h->ev_ready = nullptr;
+  h->comm_stream = nullptr;
+  h->pipeline = 0;
+}
+
+// Staged all-gather of the thin factor, overlappable with the product: stage 0 copies the own chunk into place, stage s
+// (1 <= s < G) sends the own chunk to rank (r + s) mod G and receives the chunk of rank (r - s) mod G, every link busy
+// in every stage.  ev_stage[s] fires when the chunk of rank (r - s) mod G has landed in `full`; the product then runs
+// as G column passes in that order (spmm.cu), each waiting only for its own chunk.
+int msdp_dist_exchange_begin(manisdp_handle* h, const double* local, double* full) {
+  const int G = h->world, r = h->rank;
+  const size_t cnt = (size_t)(msdp_rows_per_rank(h->n, G) * h->ld);
+  ncclComm_t comm2 = (ncclComm_t)h->nccl_comm2;
+  CUDA_TRY(h, cudaEventRecord(h->ev_ready, h->stream));  // `local` is final, previous readers of `full` are done
+  CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  CUDA_TRY(h, cudaMemcpyAsync(full + (size_t)r * cnt, local, cnt * sizeof(double), cudaMemcpyDeviceToDevice,
+                              h->comm_stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], h->comm_stream));
+  for (int s = 1; s < G; ++s) {
+    const int dst = (r + s) % G, src = (r - s + G) % G;
+    NCCL_TRY(h, g_nccl.GroupStart());
+    NCCL_TRY(h, g_nccl.Send(local, cnt, ncclDouble, dst, comm2, h->comm_stream));
+    NCCL_TRY(h, g_nccl.Recv(full + (size_t)src * cnt, cnt, ncclDouble, src, comm2, h->comm_stream));
+    NCCL_TRY(h, g_nccl.GroupEnd());
+    CUDA_TRY(h, cudaEventRecord(h->ev_stage[(size_t)s], h->comm_stream));
+  }
+  return MANISDP_OK;
 }
 
 int msdp_dist_allgather_rows(manisdp_handle* h, const double* local, double* full) {

@@ -42,8 +42,12 @@ int msdp_sync_state(manisdp_handle* h) {
 // one Hessian product of the tCG loop: Hd = Hess[d], tail -> tcg_after_hv
 static int tcg_hv(manisdp_handle* h) {
   if (h->world > 1) {
-    MSDP_TRY(msdp_dist_allgather_rows(h, h->d, h->gatherbuf));
-    MSDP_TRY(msdp_hess_dir(h, h->d, h->Hd, TAIL_TCG_DEFER));
+    if (msdp_pipeline_ok(h)) {
+      MSDP_TRY(msdp_maxcut_hess_pipelined(h, h->d, h->Hd, 1, TAIL_TCG_DEFER));
+    } else {
+      MSDP_TRY(msdp_dist_allgather_rows(h, h->d, h->gatherbuf));
+      MSDP_TRY(msdp_hess_dir(h, h->d, h->Hd, TAIL_TCG_DEFER));
+    }
     MSDP_TRY(msdp_dist_allreduce_tmp(h, 1));
     return msdp_launch_tcg_after_hv_scalar(h);
   }

@@ -508,14 +508,37 @@ static int launch_bulk(manisdp_handle* h, const SpmmArgs& a) {
   return MANISDP_OK;
 }
 
+// one pass (a.bptr0 / a.bptr1 / a.first / a.last set by the caller)
 template <int EPI>
-static int launch_spmm(manisdp_handle* h, SpmmArgs a) {
-  MSDP_TRY(msdp_spmm_prepare(h, a.ld));
-  const int B = h->spmm_B;
+static int launch_pass(manisdp_handle* h, SpmmArgs a) {
   // bulk path: measured on B200 (profiles/r1_sweep_bulk_vs_regs.txt) it wins from ld = 128 on (7.7 vs 10.2 ms at
   // p = 128), ties at p = 64 and loses below, where four register gathers per group already cover the latency
   const bool bulk = h->spmm_use_bulk == 2 ? (a.ld >= 32) : (h->spmm_use_bulk == 1 && a.ld >= 96);
   a.slots = std::max(1, std::min(BULK_MAXSLOTS, 4096 / (a.ld * 8)));
+  if (bulk) {
+    const int vpl = row_geom(a.ld).vpl;
+    if (vpl == 1)
+      launch_bulk<1, EPI>(h, a);
+    else if (vpl == 2)
+      launch_bulk<2, EPI>(h, a);
+    else if (vpl == 4)
+      launch_bulk<4, EPI>(h, a);
+    else
+      launch_bulk<8, EPI>(h, a);
+  } else {
+    DISPATCH_GEOM(row_geom(a.ld), {
+      const int nb = rows_grid(h, a.nrows, GS);
+      k_spmm<GS, VPL, EPI><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+    });
+  }
+  KERNEL_CHECK(h);
+  return MANISDP_OK;
+}
+
+template <int EPI>
+static int launch_spmm(manisdp_handle* h, SpmmArgs a) {
+  MSDP_TRY(msdp_spmm_prepare(h, a.ld));
+  const int B = h->spmm_B;
   for (int b = 0; b < B; ++b) {
     if (B == 1) {
       a.bptr0 = h->C.rowptr;
@@ -526,23 +549,56 @@ static int launch_spmm(manisdp_handle* h, SpmmArgs a) {
     }
     a.first = (b == 0);
     a.last = (b == B - 1);
-    if (bulk) {
-      const int vpl = row_geom(a.ld).vpl;
-      if (vpl == 1)
-        launch_bulk<1, EPI>(h, a);
-      else if (vpl == 2)
-        launch_bulk<2, EPI>(h, a);
-      else if (vpl == 4)
-        launch_bulk<4, EPI>(h, a);
-      else
-        launch_bulk<8, EPI>(h, a);
-    } else {
-      DISPATCH_GEOM(row_geom(a.ld), {
-        const int nb = rows_grid(h, a.nrows, GS);
-        k_spmm<GS, VPL, EPI><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
-      });
-    }
-    KERNEL_CHECK(h);
+    MSDP_TRY(launch_pass<EPI>(h, a));
+  }
+  return MANISDP_OK;
+}
+
+// ---- exchange-overlapped product of a row-sharded handle ------------------------------------------------------------
+// The operand arrives chunk by chunk (dist.cu: msdp_dist_exchange_begin, one chunk per owner rank, the own one first);
+// the product runs as one column pass per owner chunk in arrival order, each pass waiting only for its chunk, the
+// partial rows staying in `out` (n/G rows: L2-sized at the scales where this matters), the last pass applying the
+// epilogue.  Owner chunks are column blocks of width ceil(n/G), so the pass pointers are built once per handle.
+static int owner_ptrs(manisdp_handle* h) {
+  if (h->owner_bptr) return MANISDP_OK;
+  const int G = h->world;
+  CUDA_TRY(h, cudaMalloc((void**)&h->owner_bptr, (size_t)(G + 1) * (size_t)h->nloc * sizeof(int)));
+  k_block_ptrs<<<std::max(1, (int)std::min<int64_t>(h->num_sms * 8, (h->nloc + 255) / 256)), 256, 0, h->stream>>>(
+      h->C.rowptr, h->C.col, h->nloc, msdp_rows_per_rank(h->n, G), G, h->owner_bptr);
+  KERNEL_CHECK(h);
+  return MANISDP_OK;
+}
+
+bool msdp_pipeline_ok(const manisdp_handle* h) { return h->world > 1 && h->pipeline && h->C_sorted; }
+
+int msdp_maxcut_hess_pipelined(manisdp_handle* h, const double* Down, double* Hout, int from_state, int tail_mode) {
+  MSDP_TRY(owner_ptrs(h));
+  MSDP_TRY(msdp_dist_exchange_begin(h, Down, h->gatherbuf));
+  SpmmArgs a{};
+  a.col = h->C.col;
+  a.val = h->C.val;
+  a.nrows = h->nloc;
+  a.ld = (int)h->ld;
+  a.v = msdp_vecptrs(h);
+  a.st = h->st;
+  a.partials = h->partials;
+  a.sharded = 1;
+  a.Ug = h->gatherbuf;
+  a.Uown = Down;
+  a.out = Hout;
+  a.sel = from_state ? 1 : 0;
+  a.Y = h->Ybuf[h->pt];
+  a.eG = h->eG[h->pt];
+  a.mode = tail_mode;
+  const int G = h->world, r = h->rank;
+  for (int s = 0; s < G; ++s) {
+    const int q = (r - s + G) % G;
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_stage[(size_t)s], 0));
+    a.bptr0 = h->owner_bptr + (size_t)q * h->nloc;
+    a.bptr1 = h->owner_bptr + (size_t)(q + 1) * h->nloc;
+    a.first = (s == 0);
+    a.last = (s == G - 1);
+    MSDP_TRY(launch_pass<EPI_HESS>(h, a));
   }
   return MANISDP_OK;
 }
