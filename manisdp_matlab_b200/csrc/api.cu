@@ -99,6 +99,7 @@ int msdp_resize(manisdp_handle* h, int64_t p) {
     }
     h->cap_elems = cap;
     msdp_invalidate_graph(h);
+    MSDP_TRY(msdp_dist_ipc_refresh(h));
   }
   if (p != h->p) msdp_invalidate_graph(h);
   h->y_version++;

@@ -144,8 +144,11 @@ struct manisdp_handle {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_ready = nullptr;
   std::vector<cudaEvent_t> ev_stage;
-  int pipeline = 0;
+  int pipeline = 0;                     // 0 off, 1 NCCL point-to-point stages, 2 peer-memory (CUDA IPC) copy stages
   int* owner_bptr = nullptr;
+  int ipc_ready = 0;                    // all ranks mapped all peers (decided collectively in msdp_dist_ipc_refresh)
+  void* ipc_dev = nullptr;              // device scratch: world x 128 bytes of IPC handles + one barrier double
+  std::vector<double*> peer_d, peer_u;  // peers' direction array / SLOT_U mapped into this process
   std::string err;
 };
 

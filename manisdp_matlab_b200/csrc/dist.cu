@@ -82,11 +82,12 @@ int msdp_dist_init(manisdp_handle* h, const void* unique_id) {
   h->nccl_comm = (void*)comm;
   // Pipelined exchange (see msdp_dist_exchange_begin): its point-to-point stages run on their own stream and their own
   // communicator, so they can overlap the scalar all-reduces and the product passes of the main stream.
-  // Measured on B200 x2 / x8 (profiles/r1_pipelined_exchange.txt): correct, but NCCL's point-to-point stages move a
-  // 64 MB chunk far slower than its all-gather moves the whole factor (5.98 ms vs 1.25 ms per product at N = 8; 2.58 vs
-  // 2.40 ms at N = 2), so the staged path is opt-in (MANISDP_PIPELINE=1) until the stages are peer copies of our own.
+  // Measured on B200 x2 / x8 (profiles/r1_pipelined_exchange.txt), product + exchange per Hessian product:
+  //   plain ncclAllGather then one SpMM            2.40 ms (N = 2)   1.25 ms (N = 8)
+  //   mode 1: NCCL send/recv stages + passes       2.58 ms           5.98 ms   (p2p stages far below all-gather rate)
+  //   mode 2: peer-memory copy stages + passes     1.93 ms           0.83 ms   <- default
   const char* ep = getenv("MANISDP_PIPELINE");
-  const int want = ep ? atoi(ep) : 0;
+  const int want = ep ? atoi(ep) : 2;
   if (want && g_nccl.CommSplit && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd) {
     ncclComm_t comm2 = nullptr;
     if (g_nccl.CommSplit(comm, 0, h->rank, &comm2, nullptr) == ncclSuccess && comm2) {
@@ -95,14 +96,83 @@ int msdp_dist_init(manisdp_handle* h, const void* unique_id) {
       CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
       h->ev_stage.resize((size_t)h->world);
       for (auto& e : h->ev_stage) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      h->pipeline = 1;
+      h->pipeline = want >= 2 ? 2 : 1;  // 2: stages are peer-memory copies over CUDA IPC mappings (below)
+      if (h->pipeline == 2) {
+        CUDA_TRY(h, cudaMalloc((void**)&h->ipc_dev, (size_t)h->world * 128 + 8));
+        CUDA_TRY(h, cudaMemset(h->ipc_dev, 0, (size_t)h->world * 128 + 8));
+        h->peer_d.assign((size_t)h->world, nullptr);
+        h->peer_u.assign((size_t)h->world, nullptr);
+      }
     }
   }
   return MANISDP_OK;
 }
 
+static void ipc_close(manisdp_handle* h) {
+  for (auto& p : h->peer_d)
+    if (p) cudaIpcCloseMemHandle(p), p = nullptr;
+  for (auto& p : h->peer_u)
+    if (p) cudaIpcCloseMemHandle(p), p = nullptr;
+}
+
+// (Re)publish the exchange sources after the work arrays were (re)allocated: every rank exports IPC handles of its
+// direction array `d` and of SLOT_U, the handles travel through one 128-byte-per-rank NCCL all-gather, and every rank
+// maps its peers' arrays.  Collective: all ranks resize in lock-step (the drivers change p on all ranks alike).
+int msdp_dist_ipc_refresh(manisdp_handle* h) {
+  if (h->world <= 1 || h->pipeline != 2) return MANISDP_OK;
+  h->ipc_ready = 0;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->comm_stream) CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
+  ipc_close(h);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  unsigned char mine[128];
+  memset(mine, 0, sizeof(mine));
+  cudaIpcMemHandle_t hd, hu;
+  // a failure to export / map is not an error of the solve: every rank reports it and all fall back to the plain
+  // all-gather together (the decision must be collective, the two paths issue different NCCL calls)
+  double ok_local = 1.0;
+  if (cudaIpcGetMemHandle(&hd, h->d) != cudaSuccess || cudaIpcGetMemHandle(&hu, h->Uslot) != cudaSuccess) {
+    ok_local = 0.0;
+    cudaGetLastError();
+  } else {
+    memcpy(mine, &hd, 64);
+    memcpy(mine + 64, &hu, 64);
+  }
+  unsigned char* dev = (unsigned char*)h->ipc_dev;
+  CUDA_TRY(h, cudaMemcpyAsync(dev + (size_t)h->rank * 128, mine, 128, cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(h, g_nccl.AllGather(dev + (size_t)h->rank * 128, dev, 128, ncclChar, (ncclComm_t)h->nccl_comm, h->stream));
+  std::vector<unsigned char> all((size_t)h->world * 128);
+  CUDA_TRY(h, cudaMemcpyAsync(all.data(), dev, all.size(), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < h->world; ++q) {
+    if (q == h->rank) continue;
+    cudaIpcMemHandle_t a, b;
+    memcpy(&a, &all[(size_t)q * 128], 64);
+    memcpy(&b, &all[(size_t)q * 128 + 64], 64);
+    if (ok_local == 0.0) continue;
+    if (cudaIpcOpenMemHandle((void**)&h->peer_d[(size_t)q], a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle((void**)&h->peer_u[(size_t)q], b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ok_local = 0.0;
+      cudaGetLastError();
+    }
+  }
+  double* bar = (double*)(dev + (size_t)h->world * 128);
+  CUDA_TRY(h, cudaMemcpyAsync(bar, &ok_local, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(h, g_nccl.AllReduce(bar, bar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+  double ok_all = 0.0;
+  CUDA_TRY(h, cudaMemcpyAsync(&ok_all, bar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(bar, 0, sizeof(double), h->stream));
+  h->ipc_ready = (ok_all > (double)h->world - 0.5) ? 1 : 0;
+  if (!h->ipc_ready) ipc_close(h);
+  return MANISDP_OK;
+}
+
 void msdp_dist_destroy(manisdp_handle* h) {
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  ipc_close(h);
+  if (h->ipc_dev) cudaFree(h->ipc_dev);
+  h->ipc_dev = nullptr;
   if (h->nccl_comm2 && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm2);
   if (h->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
   h->nccl_comm = h->nccl_comm2 = nullptr;
@@ -124,6 +194,37 @@ int msdp_dist_exchange_begin(manisdp_handle* h, const double* local, double* ful
   const int G = h->world, r = h->rank;
   const size_t cnt = (size_t)(msdp_rows_per_rank(h->n, G) * h->ld);
   ncclComm_t comm2 = (ncclComm_t)h->nccl_comm2;
+  // peer-copy stages: rank r PULLS the chunk of rank (r - s) mod G straight out of that rank's memory (NVLink, copy
+  // engine).  The pull is not ordered by the owner's stream, so a one-double all-reduce on the main stream first acts
+  // as the "every rank has finished writing its operand" barrier; the owner cannot overwrite the operand before all
+  // pulls are done because its next writer comes after the product's own scalar all-reduce, which every rank enters
+  // only after its last pass, i.e. after its last pull.
+  const std::vector<double*>* peers = nullptr;
+  if (h->pipeline == 2) {
+    if (local == h->d) peers = &h->peer_d;
+    if (local == h->Uslot) peers = &h->peer_u;
+    if (peers) {
+      bool mapped = true;
+      for (int q = 0; q < G; ++q) mapped = mapped && (q == r || (*peers)[(size_t)q] != nullptr);
+      if (!mapped) peers = nullptr;
+    }
+  }
+  if (peers) {
+    double* bar = (double*)((unsigned char*)h->ipc_dev + (size_t)G * 128);
+    NCCL_TRY(h, g_nccl.AllReduce(bar, bar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_ready, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(full + (size_t)r * cnt, local, cnt * sizeof(double), cudaMemcpyDeviceToDevice,
+                                h->comm_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], h->comm_stream));
+    for (int s = 1; s < G; ++s) {
+      const int src = (r - s + G) % G;
+      CUDA_TRY(h, cudaMemcpyAsync(full + (size_t)src * cnt, (*peers)[(size_t)src], cnt * sizeof(double),
+                                  cudaMemcpyDefault, h->comm_stream));
+      CUDA_TRY(h, cudaEventRecord(h->ev_stage[(size_t)s], h->comm_stream));
+    }
+    return MANISDP_OK;
+  }
   CUDA_TRY(h, cudaEventRecord(h->ev_ready, h->stream));  // `local` is final, previous readers of `full` are done
   CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
   CUDA_TRY(h, cudaMemcpyAsync(full + (size_t)r * cnt, local, cnt * sizeof(double), cudaMemcpyDeviceToDevice,

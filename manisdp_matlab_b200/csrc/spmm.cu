@@ -569,7 +569,9 @@ static int owner_ptrs(manisdp_handle* h) {
   return MANISDP_OK;
 }
 
-bool msdp_pipeline_ok(const manisdp_handle* h) { return h->world > 1 && h->pipeline && h->C_sorted; }
+bool msdp_pipeline_ok(const manisdp_handle* h) {
+  return h->world > 1 && h->C_sorted && (h->pipeline == 1 || (h->pipeline == 2 && h->ipc_ready));
+}
 
 int msdp_maxcut_hess_pipelined(manisdp_handle* h, const double* Down, double* Hout, int from_state, int tail_mode) {
   MSDP_TRY(owner_ptrs(h));
