@@ -86,6 +86,7 @@ int msdp_resize(manisdp_handle* h, int64_t p) {
     const size_t cap = (size_t)rows_alloc(h) * (size_t)ld_cap;
     double** arrs[] = {&h->Ybuf[0], &h->Ybuf[1], &h->Gbuf[0], &h->Gbuf[1], &h->eta[0], &h->eta[1],
                        &h->r,       &h->d,       &h->Hd,      &h->Uslot,   &h->Hslot};
+    MSDP_TRY(msdp_dist_ipc_release(h));  // peers unmap the old arrays before they are freed
     for (double** a : arrs) {
       if (*a) cudaFree(*a);
       *a = nullptr;

@@ -115,6 +115,20 @@ static void ipc_close(manisdp_handle* h) {
     if (p) cudaIpcCloseMemHandle(p), p = nullptr;
 }
 
+// Collective: drop every mapping of peer memory and wait until all ranks have done so.  Must run BEFORE an exported
+// array is freed (resize with reallocation, destroy): freeing memory that a peer still has mapped is undefined.
+int msdp_dist_ipc_release(manisdp_handle* h) {
+  if (h->world <= 1 || h->pipeline != 2 || !h->ipc_dev || !h->nccl_comm) return MANISDP_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->comm_stream) CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
+  ipc_close(h);
+  h->ipc_ready = 0;
+  double* bar = (double*)((unsigned char*)h->ipc_dev + (size_t)h->world * 128);
+  NCCL_TRY(h, g_nccl.AllReduce(bar, bar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MANISDP_OK;
+}
+
 // (Re)publish the exchange sources after the work arrays were (re)allocated: every rank exports IPC handles of its
 // direction array `d` and of SLOT_U, the handles travel through one 128-byte-per-rank NCCL all-gather, and every rank
 // maps its peers' arrays.  Collective: all ranks resize in lock-step (the drivers change p on all ranks alike).
@@ -170,6 +184,7 @@ int msdp_dist_ipc_refresh(manisdp_handle* h) {
 
 void msdp_dist_destroy(manisdp_handle* h) {
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  msdp_dist_ipc_release(h);  // every rank unmaps before any rank frees (the arrays are freed after this returns)
   ipc_close(h);
   if (h->ipc_dev) cudaFree(h->ipc_dev);
   h->ipc_dev = nullptr;

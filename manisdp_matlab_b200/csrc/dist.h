@@ -17,6 +17,8 @@ int msdp_dist_finish_init(manisdp_handle* h);
 inline int64_t msdp_rows_per_rank(int64_t n, int world) { return world > 1 ? (n + world - 1) / world : n; }
 // collective, after the work arrays were (re)allocated: export / map the exchange sources (pipeline mode 2)
 int msdp_dist_ipc_refresh(manisdp_handle* h);
+// collective, BEFORE exported arrays are freed: unmap all peer memory and wait for every rank to have done so
+int msdp_dist_ipc_release(manisdp_handle* h);
 // staged all-gather on the exchange stream; ev_stage[s] fires when the chunk of rank (r - s) mod G is in `full`
 int msdp_dist_exchange_begin(manisdp_handle* h, const double* local, double* full);
 // dst[world*count] <- all-gather of src[count] (eigen step blocks)

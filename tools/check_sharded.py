@@ -37,6 +37,12 @@ def main():
     Yloc = h.get_Y()
     k = h.kkt(4, 1e-8, 0)
     r_cut, _ = h.rank_cut(1e-1, apply=False)
+    # second phase: a wider factor forces a reallocation of the work arrays (peer mappings are re-published)
+    p2 = 3 * p
+    Y2 = np.random.default_rng(7).standard_normal((n, p2))
+    Y2 /= np.linalg.norm(Y2, axis=1, keepdims=True)
+    h.set_Y(Y2[r0:r1])
+    info2 = h.tr_solve(maxiter=3, maxinner=10, tolgradnorm=1e-9, use_graph=0)
     h.close()
     parts = [None] * world
     dist.all_gather_object(parts, Yloc)
@@ -51,12 +57,15 @@ def main():
             Y1 = h1.get_Y()
             k1 = h1.kkt(4, 1e-8, 0)
             r1c, _ = h1.rank_cut(1e-1, apply=False)
+            h1.set_Y(Y2)
+            info21 = h1.tr_solve(maxiter=3, maxinner=10, tolgradnorm=1e-9, use_graph=0)
         errY = np.linalg.norm(Ysh - Y1) / np.linalg.norm(Y1)
         same_path = [(a[2], a[3], a[4]) for a in log] == [(a[2], a[3], a[4]) for a in log1]
         errc = max(abs(a[0] - b[0]) / abs(b[0]) for a, b in zip(log, log1))
         ok = (abs(f - f1) <= 1e-12 * abs(f1) and same_path and errc < 1e-10 and errY < 1e-7
               and info.hv_count == info1.hv_count and abs(k.dinf - k1.dinf) <= 1e-3 * abs(k1.dinf) + 1e-9
-              and abs(k.obj - k1.obj) <= 1e-9 * abs(k1.obj) and r_cut == r1c)
+              and abs(k.obj - k1.obj) <= 1e-9 * abs(k1.obj) and r_cut == r1c
+              and info2.hv_count == info21.hv_count and abs(info2.cost - info21.cost) <= 1e-10 * abs(info21.cost))
         print(json.dumps({"sharded_check": "ok" if ok else "FAIL", "world": world, "n": n, "p": p, "errY": errY,
                           "err_cost": errc, "same_path": same_path, "hv": [int(info.hv_count), int(info1.hv_count)],
                           "dinf": [k.dinf, k1.dinf], "lam_min": [k.lam_min, k1.lam_min], "rank": [r_cut, r1c]}), flush=True)
