@@ -204,6 +204,12 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
     }
     h->C_sorted = sorted ? 1 : 0;
     h->C_far_fraction = nnz ? (double)far / (double)nnz : 0.0;
+    uint64_t remote = 0;
+    for (uint64_t e = 0; e < nnz; ++e)
+      remote += (ci[(size_t)e] < h->row_begin || ci[(size_t)e] >= h->row_end) ? 1 : 0;
+    h->C_remote_fraction = nnz ? (double)remote / (double)nnz : 0.0;
+    const char* eg = getenv("MANISDP_PEER_GATHER_MAX");
+    if (eg) h->peer_gather_max_remote = atof(eg);
   }
   out.nrows = ncols;
   out.nnz = (int64_t)nnz;
@@ -414,8 +420,7 @@ int manisdp_get_dual(manisdp_t* h, double* y, double* sigma) {
 int msdp_ensure_costgrad(manisdp_handle* h) {
   if (h->cache_valid && h->grad_valid) return MANISDP_OK;
   if (h->world > 1) {
-    MSDP_TRY(msdp_dist_allgather_rows(h, h->Ybuf[h->pt], h->gatherbuf));
-    MSDP_TRY(msdp_costgrad(h, h->pt, CG_TR_DEFER));
+    MSDP_TRY(msdp_costgrad_exchange(h, h->pt, h->pt, CG_TR_DEFER));
     MSDP_TRY(msdp_dist_allreduce_tmp(h, 2));
     MSDP_TRY(msdp_dist_finish_init(h));
   } else {
@@ -449,6 +454,9 @@ int manisdp_hess(manisdp_t* h) {
   MSDP_TRY(msdp_ensure_costgrad(h));
   if (msdp_pipeline_ok(h)) {
     MSDP_TRY(msdp_maxcut_hess_pipelined(h, h->Uslot, h->Hslot, 0, TAIL_NONE));
+    // peers may read SLOT_U in place (direct peer gathers): nobody returns -- and lets its caller overwrite the slot --
+    // before every rank's product has run
+    MSDP_TRY(msdp_dist_barrier(h));
   } else {
     if (h->world > 1) MSDP_TRY(msdp_dist_allgather_rows(h, h->Uslot, h->gatherbuf));
     MSDP_TRY(msdp_hess_dir(h, h->Uslot, h->Hslot, TAIL_NONE));

@@ -149,6 +149,11 @@ struct manisdp_handle {
   int ipc_ready = 0;                    // all ranks mapped all peers (decided collectively in msdp_dist_ipc_refresh)
   void* ipc_dev = nullptr;              // device scratch: world x 128 bytes of IPC handles + one barrier double
   std::vector<double*> peer_d, peer_u;  // peers' direction array / SLOT_U mapped into this process
+  std::vector<double*> peer_y[2];       // peers' point buffers
+  double** peer_tab_dev = nullptr;      // device copy of the four tables (d, SLOT_U, Ybuf[0], Ybuf[1]), G pointers each
+  const double* const* cg_peer_tab = nullptr;  // set around a cost+grad product that gathers from peers in place
+  double C_remote_fraction = 1.0;       // share of the shard's entries whose column is owned by another rank
+  double peer_gather_max_remote = 0.05; // direct peer gathers only below this share (MANISDP_PEER_GATHER_MAX)
   std::string err;
 };
 

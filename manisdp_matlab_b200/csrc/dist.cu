@@ -98,21 +98,30 @@ int msdp_dist_init(manisdp_handle* h, const void* unique_id) {
       for (auto& e : h->ev_stage) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       h->pipeline = want >= 2 ? 2 : 1;  // 2: stages are peer-memory copies over CUDA IPC mappings (below)
       if (h->pipeline == 2) {
-        CUDA_TRY(h, cudaMalloc((void**)&h->ipc_dev, (size_t)h->world * 128 + 8));
-        CUDA_TRY(h, cudaMemset(h->ipc_dev, 0, (size_t)h->world * 128 + 8));
+        CUDA_TRY(h, cudaMalloc((void**)&h->ipc_dev, (size_t)h->world * 256 + 8));  // IPC_SLOT bytes per rank + barrier
+        CUDA_TRY(h, cudaMemset(h->ipc_dev, 0, (size_t)h->world * 256 + 8));
         h->peer_d.assign((size_t)h->world, nullptr);
         h->peer_u.assign((size_t)h->world, nullptr);
+        h->peer_y[0].assign((size_t)h->world, nullptr);
+        h->peer_y[1].assign((size_t)h->world, nullptr);
       }
     }
   }
   return MANISDP_OK;
 }
 
+// Arrays every rank publishes to its peers (CUDA IPC): the tCG direction, SLOT_U and the two point buffers.
+static const int IPC_K = 4;
+static const size_t IPC_SLOT = 64 * IPC_K;  // bytes of handles per rank
+static double* ipc_local(manisdp_handle* h, int k) { return k == 0 ? h->d : k == 1 ? h->Uslot : h->Ybuf[k - 2]; }
+static std::vector<double*>& ipc_map(manisdp_handle* h, int k) {
+  return k == 0 ? h->peer_d : k == 1 ? h->peer_u : h->peer_y[k - 2];
+}
+
 static void ipc_close(manisdp_handle* h) {
-  for (auto& p : h->peer_d)
-    if (p) cudaIpcCloseMemHandle(p), p = nullptr;
-  for (auto& p : h->peer_u)
-    if (p) cudaIpcCloseMemHandle(p), p = nullptr;
+  for (int k = 0; k < IPC_K; ++k)
+    for (auto& p : ipc_map(h, k))
+      if (p) cudaIpcCloseMemHandle(p), p = nullptr;
 }
 
 // Collective: drop every mapping of peer memory and wait until all ranks have done so.  Must run BEFORE an exported
@@ -123,15 +132,15 @@ int msdp_dist_ipc_release(manisdp_handle* h) {
   if (h->comm_stream) CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
   ipc_close(h);
   h->ipc_ready = 0;
-  double* bar = (double*)((unsigned char*)h->ipc_dev + (size_t)h->world * 128);
-  NCCL_TRY(h, g_nccl.AllReduce(bar, bar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+  MSDP_TRY(msdp_dist_barrier(h));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return MANISDP_OK;
 }
 
 // (Re)publish the exchange sources after the work arrays were (re)allocated: every rank exports IPC handles of its
-// direction array `d` and of SLOT_U, the handles travel through one 128-byte-per-rank NCCL all-gather, and every rank
-// maps its peers' arrays.  Collective: all ranks resize in lock-step (the drivers change p on all ranks alike).
+// direction array `d`, of SLOT_U and of the two point buffers, the handles travel through one NCCL all-gather
+// (IPC_SLOT bytes per rank), and every rank maps its peers' arrays.  Collective: all ranks resize in lock-step (the
+// drivers change p on all ranks alike).
 int msdp_dist_ipc_refresh(manisdp_handle* h) {
   if (h->world <= 1 || h->pipeline != 2) return MANISDP_OK;
   h->ipc_ready = 0;
@@ -139,38 +148,40 @@ int msdp_dist_ipc_refresh(manisdp_handle* h) {
   if (h->comm_stream) CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
   ipc_close(h);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  unsigned char mine[128];
+  unsigned char mine[IPC_SLOT];
   memset(mine, 0, sizeof(mine));
-  cudaIpcMemHandle_t hd, hu;
   // a failure to export / map is not an error of the solve: every rank reports it and all fall back to the plain
   // all-gather together (the decision must be collective, the two paths issue different NCCL calls)
   double ok_local = 1.0;
-  if (cudaIpcGetMemHandle(&hd, h->d) != cudaSuccess || cudaIpcGetMemHandle(&hu, h->Uslot) != cudaSuccess) {
-    ok_local = 0.0;
-    cudaGetLastError();
-  } else {
-    memcpy(mine, &hd, 64);
-    memcpy(mine + 64, &hu, 64);
-  }
-  unsigned char* dev = (unsigned char*)h->ipc_dev;
-  CUDA_TRY(h, cudaMemcpyAsync(dev + (size_t)h->rank * 128, mine, 128, cudaMemcpyHostToDevice, h->stream));
-  NCCL_TRY(h, g_nccl.AllGather(dev + (size_t)h->rank * 128, dev, 128, ncclChar, (ncclComm_t)h->nccl_comm, h->stream));
-  std::vector<unsigned char> all((size_t)h->world * 128);
-  CUDA_TRY(h, cudaMemcpyAsync(all.data(), dev, all.size(), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  for (int q = 0; q < h->world; ++q) {
-    if (q == h->rank) continue;
-    cudaIpcMemHandle_t a, b;
-    memcpy(&a, &all[(size_t)q * 128], 64);
-    memcpy(&b, &all[(size_t)q * 128 + 64], 64);
-    if (ok_local == 0.0) continue;
-    if (cudaIpcOpenMemHandle((void**)&h->peer_d[(size_t)q], a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle((void**)&h->peer_u[(size_t)q], b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+  for (int k = 0; k < IPC_K; ++k) {
+    cudaIpcMemHandle_t hk;
+    if (cudaIpcGetMemHandle(&hk, ipc_local(h, k)) != cudaSuccess) {
       ok_local = 0.0;
       cudaGetLastError();
+      break;
+    }
+    memcpy(mine + 64 * k, &hk, 64);
+  }
+  unsigned char* dev = (unsigned char*)h->ipc_dev;
+  CUDA_TRY(h, cudaMemcpyAsync(dev + (size_t)h->rank * IPC_SLOT, mine, IPC_SLOT, cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(h, g_nccl.AllGather(dev + (size_t)h->rank * IPC_SLOT, dev, IPC_SLOT, ncclChar, (ncclComm_t)h->nccl_comm,
+                               h->stream));
+  std::vector<unsigned char> all((size_t)h->world * IPC_SLOT);
+  CUDA_TRY(h, cudaMemcpyAsync(all.data(), dev, all.size(), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < h->world && ok_local != 0.0; ++q) {
+    if (q == h->rank) continue;
+    for (int k = 0; k < IPC_K; ++k) {
+      cudaIpcMemHandle_t hk;
+      memcpy(&hk, &all[(size_t)q * IPC_SLOT + 64 * k], 64);
+      if (cudaIpcOpenMemHandle((void**)&ipc_map(h, k)[(size_t)q], hk, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok_local = 0.0;
+        cudaGetLastError();
+        break;
+      }
     }
   }
-  double* bar = (double*)(dev + (size_t)h->world * 128);
+  double* bar = (double*)(dev + (size_t)h->world * IPC_SLOT);
   CUDA_TRY(h, cudaMemcpyAsync(bar, &ok_local, sizeof(double), cudaMemcpyHostToDevice, h->stream));
   NCCL_TRY(h, g_nccl.AllReduce(bar, bar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
   double ok_all = 0.0;
@@ -179,6 +190,28 @@ int msdp_dist_ipc_refresh(manisdp_handle* h) {
   CUDA_TRY(h, cudaMemsetAsync(bar, 0, sizeof(double), h->stream));
   h->ipc_ready = (ok_all > (double)h->world - 0.5) ? 1 : 0;
   if (!h->ipc_ready) ipc_close(h);
+  if (h->ipc_ready) {  // device tables for the direct peer-gather kernel: table k at [k*G, (k+1)*G)
+    const int G = h->world;
+    std::vector<double*> tab((size_t)IPC_K * G);
+    for (int k = 0; k < IPC_K; ++k)
+      for (int q = 0; q < G; ++q) tab[(size_t)k * G + q] = (q == h->rank) ? ipc_local(h, k) : ipc_map(h, k)[(size_t)q];
+    if (!h->peer_tab_dev) CUDA_TRY(h, cudaMalloc((void**)&h->peer_tab_dev, tab.size() * sizeof(double*)));
+    CUDA_TRY(h, cudaMemcpy(h->peer_tab_dev, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice));
+  }
+  return MANISDP_OK;
+}
+
+const double* const* msdp_dist_peer_table(manisdp_handle* h, const double* local) {
+  if (h->pipeline != 2 || !h->ipc_ready || !h->peer_tab_dev) return nullptr;
+  for (int k = 0; k < IPC_K; ++k)
+    if (local == ipc_local(h, k)) return (const double* const*)(h->peer_tab_dev + (size_t)k * h->world);
+  return nullptr;
+}
+
+int msdp_dist_barrier(manisdp_handle* h) {
+  if (h->world <= 1 || !h->ipc_dev) return MANISDP_OK;
+  double* bar = (double*)((unsigned char*)h->ipc_dev + (size_t)h->world * IPC_SLOT);
+  NCCL_TRY(h, g_nccl.AllReduce(bar, bar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
   return MANISDP_OK;
 }
 
@@ -188,6 +221,8 @@ void msdp_dist_destroy(manisdp_handle* h) {
   ipc_close(h);
   if (h->ipc_dev) cudaFree(h->ipc_dev);
   h->ipc_dev = nullptr;
+  if (h->peer_tab_dev) cudaFree(h->peer_tab_dev);
+  h->peer_tab_dev = nullptr;
   if (h->nccl_comm2 && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm2);
   if (h->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
   h->nccl_comm = h->nccl_comm2 = nullptr;
@@ -225,8 +260,7 @@ int msdp_dist_exchange_begin(manisdp_handle* h, const double* local, double* ful
     }
   }
   if (peers) {
-    double* bar = (double*)((unsigned char*)h->ipc_dev + (size_t)G * 128);
-    NCCL_TRY(h, g_nccl.AllReduce(bar, bar, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    MSDP_TRY(msdp_dist_barrier(h));  // every rank has written its chunk
     CUDA_TRY(h, cudaEventRecord(h->ev_ready, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
     CUDA_TRY(h, cudaMemcpyAsync(full + (size_t)r * cnt, local, cnt * sizeof(double), cudaMemcpyDeviceToDevice,

@@ -19,6 +19,11 @@ inline int64_t msdp_rows_per_rank(int64_t n, int world) { return world > 1 ? (n 
 int msdp_dist_ipc_refresh(manisdp_handle* h);
 // collective, BEFORE exported arrays are freed: unmap all peer memory and wait for every rank to have done so
 int msdp_dist_ipc_release(manisdp_handle* h);
+// device table of G operand pointers (peers' arrays mapped through CUDA IPC, own entry local) for `local` = the
+// direction array or SLOT_U; NULL when the mappings are not available
+const double* const* msdp_dist_peer_table(manisdp_handle* h, const double* local);
+// one-double all-reduce on the main stream: every rank has finished writing its operand
+int msdp_dist_barrier(manisdp_handle* h);
 // staged all-gather on the exchange stream; ev_stage[s] fires when the chunk of rank (r - s) mod G is in `full`
 int msdp_dist_exchange_begin(manisdp_handle* h, const double* local, double* full);
 // dst[world*count] <- all-gather of src[count] (eigen step blocks)

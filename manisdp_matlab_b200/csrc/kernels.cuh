@@ -36,6 +36,8 @@ int msdp_maxcut_hess(manisdp_handle* h, const double* Dgather, const double* Dow
 int msdp_maxcut_costgrad(manisdp_handle* h, int which_or_neg, int cg_mode);
 // row-sharded: exchange of the operand overlapped with one column pass per owner chunk
 bool msdp_pipeline_ok(const manisdp_handle* h);
+int msdp_costgrad_exchange(manisdp_handle* h, int buf, int which, int cg_mode);
+bool msdp_peer_gather_ok(const manisdp_handle* h);  // products gather remote rows in place: a stopped iteration costs ~nothing
 int msdp_maxcut_hess_pipelined(manisdp_handle* h, const double* Down, double* Hout, int from_state, int tail_mode);
 int msdp_spmm_shift(manisdp_handle* h, const double* Vgather, const double* Vown, double* out, int k_ld,
                     const double* zdiag);

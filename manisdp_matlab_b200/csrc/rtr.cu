@@ -70,8 +70,7 @@ static int tr_tail(manisdp_handle* h) {
   MSDP_TRY(msdp_launch_retract(h, nullptr, nullptr, nullptr, 1));
   if (h->world > 1) {
     // the proposal lives in Ybuf[pt^1]; pt on the host mirrors the device between iterations
-    MSDP_TRY(msdp_dist_allgather_rows(h, h->Ybuf[h->pt ^ 1], h->gatherbuf));
-    MSDP_TRY(msdp_costgrad(h, -1, CG_TR_DEFER));
+    MSDP_TRY(msdp_costgrad_exchange(h, h->pt ^ 1, -1, CG_TR_DEFER));
     MSDP_TRY(msdp_dist_allreduce_tmp(h, 2));
     return msdp_launch_tr_decide_scalar(h);
   }
@@ -188,8 +187,7 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
   // gradient and the per-point caches (the equivalent of Manopt's StoreDB hit, getCost.m:42-55), so nothing is redone.
   if (!(h->cache_valid && h->grad_valid)) {
     if (h->world > 1) {
-      MSDP_TRY(msdp_dist_allgather_rows(h, h->Ybuf[h->pt], h->gatherbuf));
-      MSDP_TRY(msdp_costgrad(h, -2, CG_TR_DEFER));
+      MSDP_TRY(msdp_costgrad_exchange(h, h->pt, -2, CG_TR_DEFER));
       MSDP_TRY(msdp_dist_allreduce_tmp(h, 2));
       MSDP_TRY(msdp_dist_finish_init(h));
     } else {
@@ -237,9 +235,11 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
       int done = 0, issued = 0;
       // Iterations queued after tCG has stopped are no-ops for the kernels but NOT for the NCCL exchanges of a
       // row-sharded handle (an all-gather of the factor each), so those are issued one at a time: a 20 us flag read
-      // per iteration against a >= 1 ms exchange.  Single-GPU stream mode grows the chunk instead.
-      const int chunk_cap = (h->world > 1) ? 1 : 32;
-      int chunk = (h->world > 1) ? 1 : 4;
+      // per iteration against a >= 1 ms exchange.  Single-GPU stream mode grows the chunk instead, and so does the
+      // direct peer-gather path (no exchange: a stopped iteration is three tiny all-reduces and no-op kernels).
+      const bool cheap_stop = (h->world <= 1);
+      const int chunk_cap = cheap_stop ? 32 : (msdp_peer_gather_ok(h) ? 4 : 1);
+      int chunk = cheap_stop ? 4 : (msdp_peer_gather_ok(h) ? 2 : 1);
       while (!done && issued < opt.maxinner) {
         int c = chunk;
         if (c > opt.maxinner - issued) c = opt.maxinner - issued;

@@ -57,6 +57,10 @@ struct SpmmArgs {
   RtrState* st;
   double* partials;
   int mode;            // tail_mode (EPI_HESS) or cg_mode (EPI_COSTGRAD)
+  // direct peer gathers (row-sharded, graphs with locality): operand row c lives at peer_tab[c / rpr] + (c % rpr)*ld,
+  // where peer_tab[q] is rank q's operand array mapped through CUDA IPC (own entry = the local array)
+  const double* const* peer_tab;
+  int rpr;
 };
 
 struct SpmmPtrs {
@@ -198,7 +202,7 @@ __device__ __forceinline__ void spmm_tail(const SpmmArgs& a, double (&q)[2], dou
 }
 
 // ---- register-gather kernel (any ld) --------------------------------------------------------------------------------
-template <int GS, int VPL, int EPI>
+template <int GS, int VPL, int EPI, bool PEER>
 __global__ void __launch_bounds__(MSDP_THREADS) k_spmm(const SpmmArgs a) {
   __shared__ double sm[2 * 32];
   if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
@@ -212,6 +216,14 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_spmm(const SpmmArgs a) {
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
   const bool first = a.first != 0, last = a.last != 0;
   double q[2] = {0.0, 0.0};
+  // where operand row c lives: the local / gathered array, or (PEER) straight in the owner's HBM over NVLink
+  auto operand_row = [&](int c) -> const double* {
+    if (PEER) {
+      const int owner = c / a.rpr;
+      return a.peer_tab[owner] + (size_t)(c - owner * a.rpr) * ld;
+    }
+    return Ug + (size_t)c * ld;
+  };
 
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; row < a.nrows; row += ngroups) {
     const int e0 = __ldg(a.bptr0 + row), e1 = __ldg(a.bptr1 + row);
@@ -237,10 +249,10 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_spmm(const SpmmArgs a) {
                   c2 = __shfl_sync(mask, c, k + 2, GS), c3 = __shfl_sync(mask, c, k + 3, GS);
         const double w0 = __shfl_sync(mask, w, k, GS), w1 = __shfl_sync(mask, w, k + 1, GS),
                      w2 = __shfl_sync(mask, w, k + 2, GS), w3 = __shfl_sync(mask, w, k + 3, GS);
-        const double* p0 = Ug + (size_t)c0 * ld;
-        const double* p1 = Ug + (size_t)c1 * ld;
-        const double* p2 = Ug + (size_t)c2 * ld;
-        const double* p3 = Ug + (size_t)c3 * ld;
+        const double* p0 = operand_row(c0);
+        const double* p1 = operand_row(c1);
+        const double* p2 = operand_row(c2);
+        const double* p3 = operand_row(c3);
 #pragma unroll
         for (int t = 0; t < VPL; ++t) {
           const int cv = gl + GS * t;
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_spmm(const SpmmArgs a) {
       for (; k < cnt; ++k) {
         const int c0 = __shfl_sync(mask, c, k, GS);
         const double w0 = __shfl_sync(mask, w, k, GS);
-        const double* p0 = Ug + (size_t)c0 * ld;
+        const double* p0 = operand_row(c0);
 #pragma unroll
         for (int t = 0; t < VPL; ++t) {
           const int cv = gl + GS * t;
@@ -513,7 +525,7 @@ template <int EPI>
 static int launch_pass(manisdp_handle* h, SpmmArgs a) {
   // bulk path: measured on B200 (profiles/r1_sweep_bulk_vs_regs.txt) it wins from ld = 128 on (7.7 vs 10.2 ms at
   // p = 128), ties at p = 64 and loses below, where four register gathers per group already cover the latency
-  const bool bulk = h->spmm_use_bulk == 2 ? (a.ld >= 32) : (h->spmm_use_bulk == 1 && a.ld >= 96);
+  const bool bulk = !a.peer_tab && (h->spmm_use_bulk == 2 ? (a.ld >= 32) : (h->spmm_use_bulk == 1 && a.ld >= 96));
   a.slots = std::max(1, std::min(BULK_MAXSLOTS, 4096 / (a.ld * 8)));
   if (bulk) {
     const int vpl = row_geom(a.ld).vpl;
@@ -528,7 +540,10 @@ static int launch_pass(manisdp_handle* h, SpmmArgs a) {
   } else {
     DISPATCH_GEOM(row_geom(a.ld), {
       const int nb = rows_grid(h, a.nrows, GS);
-      k_spmm<GS, VPL, EPI><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+      if (a.peer_tab)
+        k_spmm<GS, VPL, EPI, true><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+      else
+        k_spmm<GS, VPL, EPI, false><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
     });
   }
   KERNEL_CHECK(h);
@@ -573,7 +588,43 @@ bool msdp_pipeline_ok(const manisdp_handle* h) {
   return h->world > 1 && h->C_sorted && (h->pipeline == 1 || (h->pipeline == 2 && h->ipc_ready));
 }
 
+bool msdp_peer_gather_ok(const manisdp_handle* h) {
+  return msdp_pipeline_ok(h) && h->pipeline == 2 && h->peer_tab_dev &&
+         h->C_remote_fraction < h->peer_gather_max_remote;
+}
+
 int msdp_maxcut_hess_pipelined(manisdp_handle* h, const double* Down, double* Hout, int from_state, int tail_mode) {
+  // Graphs with locality (few entries point outside the owned rows, e.g. the torus profile): no exchange at all --
+  // after the cross-rank "operand written" barrier the SpMM gathers the few remote rows directly from the owner's
+  // memory (peer loads over NVLink).  Without locality every shard needs ~all rows and each would cross NVLink ~nnz/n
+  // times (peer loads bypass the local L2), so the staged chunk copies + column passes below are used instead.
+  const double* const* tab = msdp_dist_peer_table(h, Down);
+  if (tab && msdp_peer_gather_ok(h)) {
+    MSDP_TRY(msdp_dist_barrier(h));
+    SpmmArgs a{};
+    a.col = h->C.col;
+    a.val = h->C.val;
+    a.nrows = h->nloc;
+    a.ld = (int)h->ld;
+    a.v = msdp_vecptrs(h);
+    a.st = h->st;
+    a.partials = h->partials;
+    a.sharded = 1;
+    a.Ug = Down;
+    a.Uown = Down;
+    a.out = Hout;
+    a.sel = from_state ? 1 : 0;
+    a.Y = h->Ybuf[h->pt];
+    a.eG = h->eG[h->pt];
+    a.mode = tail_mode;
+    a.peer_tab = tab;
+    a.rpr = (int)msdp_rows_per_rank(h->n, h->world);
+    a.bptr0 = h->C.rowptr;
+    a.bptr1 = h->C.rowptr + 1;
+    a.first = 1;
+    a.last = 1;
+    return launch_pass<EPI_HESS>(h, a);
+  }
   MSDP_TRY(owner_ptrs(h));
   MSDP_TRY(msdp_dist_exchange_begin(h, Down, h->gatherbuf));
   SpmmArgs a{};
@@ -648,7 +699,25 @@ int msdp_maxcut_costgrad(manisdp_handle* h, int which, int cg_mode) {
     a.sel = (which == -1) ? 2 : 3;
     a.Ug = h->gatherbuf;
   }
+  if (h->cg_peer_tab) {
+    a.peer_tab = h->cg_peer_tab;
+    a.rpr = (int)msdp_rows_per_rank(h->n, h->world);
+  }
   return launch_spmm<EPI_COSTGRAD>(h, a);
+}
+
+// exchange + cost/grad product of a row-sharded handle at host-known point buffer `buf` (which: as msdp_costgrad)
+int msdp_costgrad_exchange(manisdp_handle* h, int buf, int which, int cg_mode) {
+  const double* const* tab = msdp_peer_gather_ok(h) ? msdp_dist_peer_table(h, h->Ybuf[buf]) : nullptr;
+  if (!tab) {
+    MSDP_TRY(msdp_dist_allgather_rows(h, h->Ybuf[buf], h->gatherbuf));
+    return msdp_costgrad(h, which, cg_mode);
+  }
+  MSDP_TRY(msdp_dist_barrier(h));  // every rank has written its rows of the point
+  h->cg_peer_tab = tab;
+  const int rc = msdp_costgrad(h, which, cg_mode);
+  h->cg_peer_tab = nullptr;
+  return rc;
 }
 
 // out = C*V - zdiag.*V on an n x k_ld block (eigen step); zdiag may be NULL

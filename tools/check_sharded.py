@@ -19,7 +19,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, deg, p = int(os.environ.get("CHK_N", 20011)), 12, int(os.environ.get("CHK_P", 16))
-    n, ei, ej, w = P.synthetic_er(n, deg, seed=3)
+    if os.environ.get("CHK_GRAPH", "er") == "torus":  # locality: the direct peer-gather product is selected
+        n, ei, ej, w = P.synthetic_torus(int(round(n ** 0.5)), seed=3)
+    else:
+        n, ei, ej, w = P.synthetic_er(n, deg, seed=3)
     C = P.maxcut_C(n, ei, ej, w)
     rng = np.random.default_rng(0)
     Y0 = rng.standard_normal((n, p))
