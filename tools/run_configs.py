@@ -1,7 +1,7 @@
 """Time-to-KKT of BASELINE.json configs 1-4 through the drop-in drivers (measurement script, not product code: the
 SeDuMi inputs are built with the oracle's restatement of the reference's generators bqpmom / qsmom / generate_hamming).
 
-    python tools/run_configs.py [g1 g11 g32 bqp20 bqp60 qs20 qs40s theta98 theta102] [--cpu]
+    python tools/run_configs.py [g1 g11 g32 bqp20 bqp60 qs20 qs40s theta98 theta102 er:100000 torus:316] [--cpu] [--verbose]
 """
 import json
 import os
@@ -32,6 +32,16 @@ def run(name, cpu):
         opts = dict(p0=40)
         call = lambda mod, o: mod.ManiSDP_onlyunitdiag(C, o)
         n, m = C.shape[0], C.shape[0]
+    elif name.startswith("er:") or name.startswith("torus:"):  # config 5 family: er:<n> (mean degree 48), torus:<side>
+        arg = int(float(name.split(":")[1]))
+        if name.startswith("er:"):
+            nn, ei, ej, w = P.synthetic_er(arg, 48, seed=0)
+        else:
+            nn, ei, ej, w = P.synthetic_torus(arg, seed=0)
+        C = P.maxcut_C(nn, ei, ej, w)
+        opts = dict(p0=64, delta=8)
+        call = lambda mod, o: mod.ManiSDP_onlyunitdiag(C, o)
+        n, m = nn, nn
     elif name.startswith("bqp"):
         q = int(name[3:])
         d = np.load(os.path.join(GOLDEN, f"bqp_{q}_1.npz"))
@@ -63,7 +73,7 @@ def run(name, cpu):
     else:
         raise SystemExit(f"unknown config {name}")
     t_gen = time.perf_counter() - t0
-    o = dict(opts, verbose=False)
+    o = dict(opts, verbose="--verbose" in sys.argv)
     t0 = time.perf_counter()
     X, obj, data = call(M, o)
     dt = time.perf_counter() - t0
