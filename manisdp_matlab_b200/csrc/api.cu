@@ -189,6 +189,8 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
     if (em) h->spmm_block_mode = atoi(em);
     const char* eb = getenv("MANISDP_SPMM_BULK");
     if (eb) h->spmm_use_bulk = atoi(eb);
+    const char* en = getenv("MANISDP_SPMM_NARROW");
+    if (en) h->spmm_narrow = atoi(en);
     const char* el = getenv("MANISDP_L2_TARGET_MB");
     if (el && atoi(el) > 0) h->spmm_l2_target = (int64_t)atoi(el) << 20;
     const int64_t window = h->spmm_l2_target / (64 * 8);  // operand rows per L2 window at the nominal width p = 64

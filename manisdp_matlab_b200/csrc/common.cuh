@@ -130,6 +130,7 @@ struct manisdp_handle {
   int* spmm_bptr = nullptr;
   size_t spmm_bptr_cap = 0;
   int spmm_use_bulk = 1;               // 1: cp.async.bulk gather kernel for ld >= 32 ; 0: register gathers only
+  int spmm_narrow = 1;                 // 1: k_spmm_narrow for ld <= 32 (MANISDP_SPMM_NARROW=0: generic kernel everywhere)
   int spmm_block_mode = 0;             // 0 never (default), 1 auto (only for matrices without locality), 2 always
   int64_t spmm_l2_target = 64ll << 20; // bytes of operand rows per column block
   int C_sorted = 0;                    // rows of C are column-sorted

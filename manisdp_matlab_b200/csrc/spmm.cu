@@ -61,6 +61,7 @@ struct SpmmArgs {
   // where peer_tab[q] is rank q's operand array mapped through CUDA IPC (own entry = the local array)
   const double* const* peer_tab;
   int rpr;
+  int row0;            // global index of local row 0 (set by launch_pass)
 };
 
 struct SpmmPtrs {
@@ -298,6 +299,146 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_spmm(const SpmmArgs a) {
   if (last) spmm_tail<EPI>(a, q, sm);
 }
 
+// ---- register-gather kernel for narrow rows (ld <= 32: one double2 per lane, 2..16 lanes per row) ---------------------
+// Same arithmetic, entry order and results as k_spmm.  With few lanes per row a row is a chain of short dependent
+// rounds (indices -> gathers -> epilogue operands -> store), so the chain is shortened instead of widened
+// (tools/spmm_narrow_lab.cu, profiles/r1_spmm_narrow_lab.txt; 1e6 rows of 1 + Poisson(48) entries):
+//   * the indices of the next round are fetched before the gathers of the current one;
+//   * the tail of a round is padded to the unroll width with (own row, weight 0) entries -- the one-by-one remainder
+//     loop paid a full memory latency per entry (own row: the line the epilogue reads anyway, and never remote);
+//   * the epilogue operands (Y row, U row, multiplier) are requested at the start of the row.
+//   ld = 8: 0.573 -> 0.437 ms, ld = 16: 0.979 -> 0.808 ms, ld = 32: 1.761 -> 1.680 ms.  At ld = 64 (32 lanes per row,
+//   the bench configuration) the gain is inside the noise (3.60 -> 3.54 ms), so k_spmm stays as it is.
+template <int GS, int EPI, bool PEER>
+__global__ void __launch_bounds__(MSDP_THREADS, 4) k_spmm_narrow(const SpmmArgs a) {
+  __shared__ double sm[2 * 32];
+  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  const SpmmPtrs p = select_ptrs(a);
+  const int* __restrict__ col = a.col;
+  const double* __restrict__ val = a.val;
+  const double* __restrict__ Ug = p.Ug;
+  const int ld = a.ld;
+  const unsigned mask = group_mask<GS>();
+  const int gl = threadIdx.x % GS;
+  const bool act = gl < ld / 2;
+  const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
+  const bool first = a.first != 0, last = a.last != 0;
+  double q[2] = {0.0, 0.0};
+  auto operand_row = [&](int c) -> const double* {
+    if (PEER) {
+      const int owner = c / a.rpr;
+      return a.peer_tab[owner] + (size_t)(c - owner * a.rpr) * ld;
+    }
+    return Ug + (size_t)c * ld;
+  };
+
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; row < a.nrows; row += ngroups) {
+    const int e0 = __ldg(a.bptr0 + row), e1 = __ldg(a.bptr1 + row);
+    const size_t off = (size_t)row * ld + 2 * gl;
+    double2 y = make_double2(0.0, 0.0), u = make_double2(0.0, 0.0);
+    double eg = 0.0;
+    if (last) {
+      if (EPI == EPI_HESS) {
+        if (act) {
+          y = ld2(p.Y + off);
+          u = ld2(p.Uown + off);
+        }
+        eg = p.eG[row];
+      } else if (EPI == EPI_COSTGRAD) {
+        if (act) y = ld2(p.Uown + off);
+      } else {
+        if (act) u = ld2(p.Uown + off);
+        eg = p.eG ? p.eG[row] : 0.0;
+      }
+    }
+    double2 acc = (!first && act) ? ldcs2(p.out + off) : make_double2(0.0, 0.0);
+    const int padc = a.row0 + (int)row;
+    int c = padc;
+    double w = 0.0;
+    if (e0 + gl < e1) {
+      c = __ldg(col + e0 + gl);
+      w = __ldg(val + e0 + gl);
+    }
+    for (int base = e0; base < e1; base += GS) {
+      int cn = padc;
+      double wn = 0.0;
+      const int en = base + GS + gl;
+      if (en < e1) {
+        cn = __ldg(col + en);
+        wn = __ldg(val + en);
+      }
+      int cnt = min(GS, e1 - base);
+      if (GS >= 4) cnt = (cnt + 3) & ~3;  // <= GS; the extra lanes hold (own row, 0)
+      int k = 0;
+      for (; k + 4 <= cnt; k += 4) {
+        const int c0 = __shfl_sync(mask, c, k, GS), c1 = __shfl_sync(mask, c, k + 1, GS),
+                  c2 = __shfl_sync(mask, c, k + 2, GS), c3 = __shfl_sync(mask, c, k + 3, GS);
+        const double w0 = __shfl_sync(mask, w, k, GS), w1 = __shfl_sync(mask, w, k + 1, GS),
+                     w2 = __shfl_sync(mask, w, k + 2, GS), w3 = __shfl_sync(mask, w, k + 3, GS);
+        const double* p0 = operand_row(c0);
+        const double* p1 = operand_row(c1);
+        const double* p2 = operand_row(c2);
+        const double* p3 = operand_row(c3);
+        if (act) {
+          const double2 u0 = ldg2(p0 + 2 * gl), u1 = ldg2(p1 + 2 * gl), u2 = ldg2(p2 + 2 * gl), u3 = ldg2(p3 + 2 * gl);
+          acc.x = fma(w0, u0.x, acc.x);
+          acc.y = fma(w0, u0.y, acc.y);
+          acc.x = fma(w1, u1.x, acc.x);
+          acc.y = fma(w1, u1.y, acc.y);
+          acc.x = fma(w2, u2.x, acc.x);
+          acc.y = fma(w2, u2.y, acc.y);
+          acc.x = fma(w3, u3.x, acc.x);
+          acc.y = fma(w3, u3.y, acc.y);
+        }
+      }
+      for (; k < cnt; ++k) {  // GS == 2 only
+        const int c0 = __shfl_sync(mask, c, k, GS);
+        const double w0 = __shfl_sync(mask, w, k, GS);
+        if (act) {
+          const double2 u0 = ldg2(operand_row(c0) + 2 * gl);
+          acc.x = fma(w0, u0.x, acc.x);
+          acc.y = fma(w0, u0.y, acc.y);
+        }
+      }
+      c = cn;
+      w = wn;
+    }
+    if (!last) {
+      if (act) stcs2(p.out + off, acc);
+      continue;
+    }
+    if (EPI == EPI_HESS) {
+      const double dot = group_sum<GS>(act ? y.x * acc.x + y.y * acc.y : 0.0, mask);  // sum(Y.*eH), :129
+      if (act) {
+        double2 hv;
+        hv.x = acc.x - y.x * dot - u.x * eg;
+        hv.y = acc.y - y.y * dot - u.y * eg;
+        st2(p.out + off, hv);
+        q[0] += u.x * hv.x + u.y * hv.y;  // <mdelta, Hmdelta>, tCG.m:166
+      }
+    } else if (EPI == EPI_COSTGRAD) {
+      const double dot = group_sum<GS>(act ? y.x * acc.x + y.y * acc.y : 0.0, mask);  // eG(row) = sum(YC.*Y), :119
+      if (gl == 0) {
+        p.eGout[row] = dot;
+        q[0] += dot;
+      }
+      if (act) {
+        double2 g;
+        g.x = acc.x - y.x * dot;  // G = YC - Y.*eG, :124
+        g.y = acc.y - y.y * dot;
+        st2(p.out + off, g);
+        q[1] += g.x * g.x + g.y * g.y;
+      }
+    } else if (act) {  // EPI_SHIFT: out = C*V - z.*V
+      double2 o;
+      o.x = acc.x - eg * u.x;
+      o.y = acc.y - eg * u.y;
+      st2(p.out + off, o);
+    }
+  }
+  if (last) spmm_tail<EPI>(a, q, sm);
+}
+
 // ---- bulk-async gather kernel (ld >= 32, one warp per row) ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -520,6 +661,21 @@ static int launch_bulk(manisdp_handle* h, const SpmmArgs& a) {
   return MANISDP_OK;
 }
 
+template <int GS, int VPL, int EPI>
+static void launch_rows(manisdp_handle* h, const SpmmArgs& a) {
+  const int nb = rows_grid(h, a.nrows, GS);
+  if constexpr (VPL == 1 && GS <= 16) {
+    if (h->spmm_narrow && !a.peer_tab) {  // (the peer-table variant would spill at the 64-register cap)
+      k_spmm_narrow<GS, EPI, false><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+      return;
+    }
+  }
+  if (a.peer_tab)
+    k_spmm<GS, VPL, EPI, true><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+  else
+    k_spmm<GS, VPL, EPI, false><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+}
+
 // one pass (a.bptr0 / a.bptr1 / a.first / a.last set by the caller)
 template <int EPI>
 static int launch_pass(manisdp_handle* h, SpmmArgs a) {
@@ -538,13 +694,8 @@ static int launch_pass(manisdp_handle* h, SpmmArgs a) {
     else
       launch_bulk<8, EPI>(h, a);
   } else {
-    DISPATCH_GEOM(row_geom(a.ld), {
-      const int nb = rows_grid(h, a.nrows, GS);
-      if (a.peer_tab)
-        k_spmm<GS, VPL, EPI, true><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
-      else
-        k_spmm<GS, VPL, EPI, false><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
-    });
+    a.row0 = (int)h->row_begin;
+    DISPATCH_GEOM(row_geom(a.ld), { launch_rows<GS, VPL, EPI>(h, a); });
   }
   KERNEL_CHECK(h);
   return MANISDP_OK;

@@ -78,6 +78,7 @@ def ManiSDP_onlyunitdiag(C, options=None):
     t0 = time.perf_counter()
     with _lib.Handle("onlyunitdiag", n, C_csc=C, device=o["device"]) as h:
         _init_point(h, o)
+        data["setup_seconds"] = time.perf_counter() - t0
         staged = False
         dinf0 = None
         for it in range(1, int(o["AL_maxiter"]) + 1):
@@ -89,7 +90,10 @@ def ManiSDP_onlyunitdiag(C, options=None):
             data["tr_iters"] += info.iters
             data["tr_seconds"] += info.seconds
             gradnorm = info.gradnorm
+            t_k = time.perf_counter()
             k = h.kkt(int(o["delta"]), o["eig_tol"], 0)  # :45-51
+            data["kkt_seconds"] = data.get("kkt_seconds", 0.0) + time.perf_counter() - t_k
+            data["eig_iters_total"] = data.get("eig_iters_total", 0) + int(k.eig_iters)
             obj, dinf = k.obj, k.dinf
             p = h.p
             r, _ = h.rank_cut(o["theta"], apply=False)  # :52-54

@@ -81,7 +81,9 @@ def run(name, cpu):
     rec = dict(config=name, n=n, m=m, seconds=dt, obj=obj, eta=eta, iters=data["iters"], hv=int(data["hv_count"]),
                tr_seconds=data["tr_seconds"], hv_per_s=data["hv_count"] / max(data["tr_seconds"], 1e-9),
                status=data["status"], launches=int(data.get("launches", 0)), gen_seconds=t_gen,
-               modes=[data.get("s_mode"), data.get("a_mode")], p_max=max(data["fac_size"]))
+               modes=[data.get("s_mode"), data.get("a_mode")], p_max=max(data["fac_size"]),
+               kkt_seconds=data.get("kkt_seconds"), eig_iters=data.get("eig_iters_total"),
+               setup_seconds=data.get("setup_seconds"))
     if cpu:
         t0 = time.perf_counter()
         Xc, objc, dc = call(ref, dict(opts, seed=0))

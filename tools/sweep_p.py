@@ -11,10 +11,10 @@ def run(name, C, n, ps, reps):
             h.rand_Y(p, 1)
             U = np.random.default_rng(1).standard_normal((n, p))
             h.slot_set(_lib.SLOT_U, U)
-            h.hess_bench(3)
+            h.hess_bench(40)  # long enough for the SM clock to ramp after the host-side set-up above
             ms = h.hess_bench(reps)
             st = h.stats()
-            out.append(dict(graph=name, p=p, ms=ms, alg_GBps=st.bytes_per_hv / ms / 1e6,
+            out.append(dict(graph=name, p=p, narrow=os.environ.get("MANISDP_SPMM_NARROW", "1"), ms=ms, alg_GBps=st.bytes_per_hv / ms / 1e6,
                             gather_GBps=(st.nnzC * p * 8) / ms / 1e6))
             print(json.dumps(out[-1]), flush=True)
     return out
@@ -28,4 +28,8 @@ if __name__ == "__main__":
     else:
         n, ei, ej, w = P.synthetic_torus(int(round(n ** 0.5)), 0)
     C = P.maxcut_C(n, ei, ej, w)
-    run(which, C, n, ps, 10)
+    if len(sys.argv) > 4 and sys.argv[4] == "narrow_ab":  # generic kernel vs k_spmm_narrow on the same graph
+        os.environ["MANISDP_SPMM_NARROW"] = "0"
+        run(which, C, n, ps, 20)
+        os.environ["MANISDP_SPMM_NARROW"] = "1"
+    run(which, C, n, ps, 20)
