@@ -121,12 +121,13 @@ def _cpu_threads():
     return threads()
 
 
-def cpu_sample(C, n, p, maxinner, repeats=1):
-    """The oracle port on the host cores: trustregions (1 outer iteration, `maxinner` products) on the same workload."""
+def cpu_sample(C, n, p, maxinner, repeats=1, Y0=None):
+    """The oracle port on the host cores: `repeats` steps trustregions(1 outer iteration, <= `maxinner` products) on the
+    same workload, from Y0 (the point at which the GPU arm's timed region started) when given."""
     from oracle.manisdp_ref import OnlyUnitDiagProblem
     from oracle.manopt_rtr import trustregions
     Ccsr = C.tocsr()
-    Y = start_point(n, p)
+    Y = start_point(n, p) if Y0 is None else np.array(Y0, dtype=np.float64)
     hv, t = 0, 0.0
     for _ in range(repeats):
         prob = OnlyUnitDiagProblem(Ccsr, p, stale_eG=True)
@@ -228,6 +229,8 @@ def run_ours(args, rank, world):
     # ---- device-resident metric -------------------------------------------------------------------------------
     for _ in range(args.warmup):
         step()
+    # the bounded CPU sample replays the first timed steps from exactly this point
+    Y_timed_start = h.get_Y() if (world == 1 and not args.no_cpu) else None
     l0 = h.stats().launches_total
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -319,10 +322,12 @@ def run_ours(args, rank, world):
     # ---- CPU baseline (bounded sample) + config-1 time-to-KKT ----------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        chv, ct = cpu_sample(C, n, p, args.cpu_inner)
+        chv, ct = cpu_sample(C, n, p, args.cpu_inner, repeats=args.cpu_steps, Y0=Y_timed_start)
         cpu = {"value": chv / ct, "unit": UNIT, "cores": _cpu_threads(), "host_cores": os.cpu_count(), "kind": "port",
-               "sample": f"oracle port: trustregions(maxiter=1, maxinner={args.cpu_inner}) on the same instance "
-                         f"({chv} Hv + 2 cost evaluations in {ct:.1f} s; sparse*dense on {_cpu_threads()} threads)"}
+               "sample": f"oracle port replaying the first {args.cpu_steps} timed steps trustregions(maxiter=1, "
+                         f"maxinner={args.cpu_inner}) of the same instance from the point where the GPU arm's timed "
+                         f"region starts ({chv} Hv + {2 * args.cpu_steps} cost/gradient "
+                         f"evaluations in {ct:.1f} s; sparse*dense on {_cpu_threads()} threads, vector work in NumPy)"}
     kkt = None
     if world == 1 and not args.no_kkt:
         kkt = time_to_kkt()
@@ -422,13 +427,18 @@ def main():
     ap.add_argument("--inner", type=int, default=16)
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--hv-reps", type=int, default=20)
-    ap.add_argument("--cpu-inner", type=int, default=3)
-    ap.add_argument("--ref-inner", type=int, default=1)
+    ap.add_argument("--cpu-inner", type=int, default=None, help="maxinner of the CPU sample (default: --inner)")
+    ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the bounded CPU sample in the default run")
+    ap.add_argument("--ref-inner", type=int, default=None, help="maxinner of --impl reference steps (default: --inner)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kkt", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
     args = ap.parse_args()
+    if args.cpu_inner is None:
+        args.cpu_inner = args.inner
+    if args.ref_inner is None:
+        args.ref_inner = args.inner
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank = int(os.environ.get("RANK", 0))
