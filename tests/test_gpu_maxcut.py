@@ -63,6 +63,28 @@ def test_closures_match_oracle(G1, p):
         assert _rel(h.retract(0.3 * Ut), prob.M.retr(Y, 0.3 * Ut)) < 1e-13
 
 
+@pytest.mark.parametrize("p", [2, 5, 8, 12, 16, 29, 32])
+def test_narrow_row_kernel_matches_generic(G1, p, monkeypatch):
+    """k_spmm_narrow (ld <= 32, the default there) and the generic k_spmm (MANISDP_SPMM_NARROW=0) do the same
+    arithmetic in the same entry order: cost, gradient and Hessian product agree to rounding of the row dot product."""
+    from manisdp_matlab_b200 import Handle
+    n = G1.shape[0]
+    Y, rng = _rand_point(n, p, 100 + p)
+    U = rng.standard_normal((n, p))
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MANISDP_SPMM_NARROW", flag)
+        with Handle("onlyunitdiag", n, C_csc=G1) as h:
+            h.set_Y(Y)
+            f = h.cost()
+            g, gn = h.grad()
+            out[flag] = (f, g.copy(), gn, h.hess(U).copy())
+    assert abs(out["1"][0] - out["0"][0]) <= 1e-14 * abs(out["0"][0])
+    assert _rel(out["1"][1], out["0"][1]) < 1e-14
+    assert abs(out["1"][2] - out["0"][2]) <= 1e-14 * out["0"][2]
+    assert _rel(out["1"][3], out["0"][3]) < 1e-14
+
+
 def test_nonsymmetric_and_empty_rows():
     """column lists of C are used as row lists: (Y*C)(:,j) = sum_i C(i,j) Y(:,i) also for a non-symmetric C with
     empty columns and an isolated vertex (ragged input)."""
