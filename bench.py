@@ -304,6 +304,9 @@ def run_ours(args, rank, world):
                 "traffic": args.traffic, "algorithmic_bytes_per_launch": st.bytes_per_hv,
                 "ms_per_launch": ms, "gflops": st.flops_per_hv / (ms * 1e-3) / 1e9,
                 "includes_allgather": world > 1}
+    if args.traffic:  # how busy HBM actually is: measured DRAM bytes per launch (ncu) over the live launch time
+        roofline["traffic_GBps"] = args.traffic / (ms * 1e-3) / 1e9
+        roofline["traffic_frac_of_peak"] = roofline["traffic_GBps"] / peak
     # the fused vector kernels of the loop (K5-K7), same roofline arithmetic
     vec = None
     if world == 1:
