@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) k_v0(const int* __restrict__ rowptr, cons
 // one pass over the entry stream of one column block; chunk_ptr[ch] .. chunk_ptr[ch+1] = entries of chunk ch.
 // Register diet: only the U gathered vectors stay live across the loads; weights are broadcast when consumed and row
 // changes are a ballot mask computed once per group of 32 entries.
-template <int U, int MINB>
+template <int U, int MINB, bool RMW>
 __global__ void __launch_bounds__(256, MINB) k_bm(const int* __restrict__ ecol, const double* __restrict__ eval_,
                                                   const int* __restrict__ erow, const int* __restrict__ chunk_ptr,
                                                   int nchunks, const double* __restrict__ Ug, double* __restrict__ out) {
@@ -98,12 +98,12 @@ __global__ void __launch_bounds__(256, MINB) k_bm(const int* __restrict__ ecol, 
         for (int s = 0; s < U; ++s) {
           if ((chg >> (k + s)) & 1u) {  // warp-uniform
             if (cur >= 0) {
-              old.x += acc.x; old.y += acc.y;
+              if (RMW) { old.x += acc.x; old.y += acc.y; } else { old = acc; }
               reinterpret_cast<double2*>(out + (size_t)cur * LD)[lane] = old;
             }
             cur = __shfl_sync(0xffffffffu, r, k + s);
             acc = make_double2(0.0, 0.0);
-            old = reinterpret_cast<const double2*>(out + (size_t)cur * LD)[lane];
+            if (RMW) old = reinterpret_cast<const double2*>(out + (size_t)cur * LD)[lane];
           }
           const double ws = __shfl_sync(0xffffffffu, w, k + s);
           acc.x = fma(ws, u[s].x, acc.x);
@@ -113,9 +113,27 @@ __global__ void __launch_bounds__(256, MINB) k_bm(const int* __restrict__ ecol, 
       c = cn; w = wn; r = rn;
     }
     if (cur >= 0) {
-      old.x += acc.x; old.y += acc.y;
+      if (RMW) { old.x += acc.x; old.y += acc.y; } else { old = acc; }
       reinterpret_cast<double2*>(out + (size_t)cur * LD)[lane] = old;
     }
+  }
+}
+
+// !RMW variant: pass b stores its partial rows into part[b] (no read, so no dependent load in the pass); this pass adds
+// the partial rows a row actually has (bit b of mask[row]) -- in the product it would carry the projection epilogue
+__global__ void __launch_bounds__(256) k_sum(const double* __restrict__ part, const unsigned* __restrict__ mask, int B,
+                                             long n, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long nw = (long)gridDim.x * 8;
+  for (long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += nw) {
+    const unsigned m = __ldg(mask + row);
+    double2 acc = make_double2(0.0, 0.0);
+    for (int b = 0; b < B; ++b)
+      if ((m >> b) & 1u) {
+        const double2 v = __ldcs(reinterpret_cast<const double2*>(part + ((size_t)b * n + row) * LD) + lane);
+        acc.x += v.x; acc.y += v.y;
+      }
+    reinterpret_cast<double2*>(out + (size_t)row * LD)[lane] = acc;
   }
 }
 
@@ -123,6 +141,7 @@ struct BlockMajor {
   int B = 0;
   int *ecol = nullptr, *erow = nullptr, *chunk_ptr = nullptr;
   double* eval_ = nullptr;
+  unsigned* mask = nullptr;  // per row: which blocks hold entries of it
   std::vector<int> chunk_off;  // per block: first chunk index (B + 1 entries)
 };
 
@@ -138,10 +157,12 @@ static BlockMajor build(const std::vector<int>& rp, const std::vector<int>& ci, 
   std::vector<int> ecol(nnz), erow(nnz);
   std::vector<double> ev(nnz);
   std::vector<long> pos(cntb.begin(), cntb.end() - 1);
+  std::vector<unsigned> hmask(n, 0u);
   for (long i = 0; i < n; ++i)
     for (int e = rp[i]; e < rp[i + 1]; ++e) {
       const long q = pos[ci[e] / jrows]++;
       ecol[q] = ci[e]; erow[q] = (int)i; ev[q] = va[e];
+      hmask[i] |= 1u << (ci[e] / jrows);
     }
   // row-aligned chunks of about chunk_target entries inside each block
   std::vector<int> cptr;
@@ -166,27 +187,32 @@ static BlockMajor build(const std::vector<int>& rp, const std::vector<int>& ci, 
   CK(cudaMemcpy(bm.erow, erow.data(), nnz * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(bm.eval_, ev.data(), nnz * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(bm.chunk_ptr, cptr.data(), cptr.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&bm.mask, n * 4));
+  CK(cudaMemcpy(bm.mask, hmask.data(), n * 4, cudaMemcpyHostToDevice));
   return bm;
 }
 
 static void release(BlockMajor& bm) {
-  cudaFree(bm.ecol); cudaFree(bm.erow); cudaFree(bm.eval_); cudaFree(bm.chunk_ptr);
+  cudaFree(bm.ecol); cudaFree(bm.erow); cudaFree(bm.eval_); cudaFree(bm.chunk_ptr); cudaFree(bm.mask);
 }
 
-template <int U, int MINB>
-static float run_bm(const BlockMajor& bm, const double* Ug, double* out, long n, int sms, int reps, int* regs, int* occ) {
-  auto kern = k_bm<U, MINB>;
+template <int U, int MINB, bool RMW>
+static float run_bm(const BlockMajor& bm, const double* Ug, double* out, double* part, long n, int sms, int reps,
+                    int* regs, int* occ) {
+  auto kern = k_bm<U, MINB, RMW>;
   cudaFuncAttributes fa;
   cudaFuncGetAttributes(&fa, kern);
   *regs = fa.numRegs;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, 256, 0);
   const int grid = sms * std::max(1, *occ);
   auto once = [&]() {
-    cudaMemsetAsync(out, 0, (size_t)n * LD * 8);
+    if (RMW) cudaMemsetAsync(out, 0, (size_t)n * LD * 8);
     for (int b = 0; b < bm.B; ++b) {
       const int nch = bm.chunk_off[b + 1] - bm.chunk_off[b];
-      kern<<<grid, 256>>>(bm.ecol, bm.eval_, bm.erow, bm.chunk_ptr + bm.chunk_off[b], nch, Ug, out);
+      kern<<<grid, 256>>>(bm.ecol, bm.eval_, bm.erow, bm.chunk_ptr + bm.chunk_off[b], nch, Ug,
+                          RMW ? out : part + (size_t)b * n * LD);
     }
+    if (!RMW) k_sum<<<sms * 8, 256>>>(part, bm.mask, bm.B, n, out);
   };
   once();
   CK(cudaDeviceSynchronize());
@@ -248,27 +274,28 @@ int main(int argc, char** argv) {
   fflush(stdout);
   std::vector<double> h0((size_t)n * LD), h1((size_t)n * LD);
   CK(cudaMemcpy(h0.data(), o0, h0.size() * 8, cudaMemcpyDeviceToHost));
-  auto report = [&](int B, int chunk, int U, int minb, int regs, int occ, float ms) {
+  double* part = nullptr;
+  CK(cudaMalloc(&part, (size_t)8 * n * LD * 8));  // partial rows of up to 8 blocks
+  auto report = [&](int B, int chunk, int U, int minb, int regs, int occ, float ms, int rmw = 1) {
     CK(cudaMemcpy(h1.data(), o1, h1.size() * 8, cudaMemcpyDeviceToHost));
     double md = 0;
     for (size_t i = 0; i < h0.size(); i += 61) md = std::max(md, fabs(h0[i] - h1[i]));
     printf("{\"variant\": \"block_major\", \"B\": %d, \"chunk\": %d, \"u\": %d, \"minb\": %d, \"regs\": %d, "
-           "\"blocks_per_sm\": %d, \"ms\": %.3f, \"maxdiff\": %.2e}\n", B, chunk, U, minb, regs, occ, ms, md);
+           "\"blocks_per_sm\": %d, \"rmw\": %d, \"ms\": %.3f, \"maxdiff\": %.2e}\n", B, chunk, U, minb, regs, occ, rmw, ms, md);
     fflush(stdout);
   };
-  const int Bs[] = {4, 8, 12, 16};
+  const int Bs[] = {2, 3, 4, 6, 8};
   for (int B : Bs) {
-    for (int chunk : {224, 480}) {
-      BlockMajor bm = build(rp, ci, va, n, B, chunk);
-      int regs, occ;
-      float ms;
-      ms = run_bm<4, 6>(bm, Ug, o1, n, sms, 5, &regs, &occ); report(B, chunk, 4, 6, regs, occ, ms);
-      ms = run_bm<4, 4>(bm, Ug, o1, n, sms, 5, &regs, &occ); report(B, chunk, 4, 4, regs, occ, ms);
-      ms = run_bm<8, 4>(bm, Ug, o1, n, sms, 5, &regs, &occ); report(B, chunk, 8, 4, regs, occ, ms);
-      ms = run_bm<8, 5>(bm, Ug, o1, n, sms, 5, &regs, &occ); report(B, chunk, 8, 5, regs, occ, ms);
-      if (chunk == 224) { ms = run_bm<16, 3>(bm, Ug, o1, n, sms, 5, &regs, &occ); report(B, chunk, 16, 3, regs, occ, ms); }
-      release(bm);
-    }
+    BlockMajor bm = build(rp, ci, va, n, B, 224);
+    int regs, occ;
+    float ms;
+    ms = run_bm<4, 4, true>(bm, Ug, o1, part, n, sms, 5, &regs, &occ); report(B, 224, 4, 4, regs, occ, ms, 1);
+    ms = run_bm<4, 4, false>(bm, Ug, o1, part, n, sms, 5, &regs, &occ); report(B, 224, 4, 4, regs, occ, ms, 0);
+    ms = run_bm<4, 5, false>(bm, Ug, o1, part, n, sms, 5, &regs, &occ); report(B, 224, 4, 5, regs, occ, ms, 0);
+    ms = run_bm<4, 6, false>(bm, Ug, o1, part, n, sms, 5, &regs, &occ); report(B, 224, 4, 6, regs, occ, ms, 0);
+    ms = run_bm<8, 4, false>(bm, Ug, o1, part, n, sms, 5, &regs, &occ); report(B, 224, 8, 4, regs, occ, ms, 0);
+    ms = run_bm<8, 3, false>(bm, Ug, o1, part, n, sms, 5, &regs, &occ); report(B, 224, 8, 3, regs, occ, ms, 0);
+    release(bm);
   }
   return 0;
 }
