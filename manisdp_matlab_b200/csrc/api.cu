@@ -102,6 +102,16 @@ int msdp_resize(manisdp_handle* h, int64_t p) {
     msdp_invalidate_graph(h);
     MSDP_TRY(msdp_dist_ipc_refresh(h));
   }
+  if (h->bm_B > 0 && ld > 32 && ld <= 64) {  // partial rows of the block-major product (spmm.cu: launch_bm)
+    const size_t want = (size_t)h->bm_B * (size_t)rows_alloc(h) * 64;
+    if (h->bm_part_cap < want) {
+      if (h->bm_part) cudaFree(h->bm_part);
+      h->bm_part = nullptr;
+      CUDA_TRY(h, cudaMalloc((void**)&h->bm_part, want * sizeof(double)));
+      h->bm_part_cap = want;
+      msdp_invalidate_graph(h);
+    }
+  }
   if (p != h->p) msdp_invalidate_graph(h);
   h->y_version++;
   h->p = p;
@@ -169,6 +179,67 @@ static int download_rows(manisdp_handle* h, const double* src, double* dst, int3
 }
 
 // ---- create / destroy ----------------------------------------------------------------------------------------------
+// Block-major copy of the row lists (rp, ci, val) for spmm.cu:launch_bm.  Operand rows are cut into B column blocks
+// (about 2 x the L2 target at the nominal width p = 64, at most 8 blocks); the entries are stored block by block, inside
+// a block row by row in their original order, as (col, val, row); every block is cut into row-aligned chunks of about
+// BM_CHUNK entries (one chunk = the work of one warp).  All index work is integer and exact.
+#define BM_CHUNK 224
+static int build_block_major(manisdp_handle* h, const std::vector<int>& rp, const std::vector<int>& ci,
+                             const double* val, int64_t nrows) {
+  const int64_t nnz = (int64_t)ci.size();
+  const int64_t ncols_op = h->n;  // operand rows = global columns of C
+  int B;
+  if (h->bm_mode == 2 && ncols_op * 512 < 4 * h->spmm_l2_target)
+    B = 3;  // forced on a small instance (tests): still several blocks
+  else
+    B = (int)std::min<int64_t>(8, std::max<int64_t>(2, (ncols_op * 512 + 2 * h->spmm_l2_target - 1) /
+                                                           (2 * h->spmm_l2_target)));
+  const int64_t jrows = (ncols_op + B - 1) / B;
+  std::vector<int64_t> start((size_t)B + 1, 0);
+  for (int64_t e = 0; e < nnz; ++e) start[(size_t)(ci[(size_t)e] / jrows) + 1]++;
+  for (int b = 0; b < B; ++b) start[(size_t)b + 1] += start[(size_t)b];
+  std::vector<int> ecol((size_t)nnz), erow((size_t)nnz);
+  std::vector<double> ev((size_t)nnz);
+  std::vector<unsigned> mask((size_t)nrows, 0u);
+  std::vector<int64_t> pos(start.begin(), start.end() - 1);
+  for (int64_t i = 0; i < nrows; ++i)
+    for (int e = rp[(size_t)i]; e < rp[(size_t)i + 1]; ++e) {
+      const int b = (int)(ci[(size_t)e] / jrows);
+      const int64_t q = pos[(size_t)b]++;
+      ecol[(size_t)q] = ci[(size_t)e];
+      erow[(size_t)q] = (int)i;
+      ev[(size_t)q] = val[e];
+      mask[(size_t)i] |= 1u << b;
+    }
+  std::vector<int> cptr;
+  h->bm_chunk_off.assign((size_t)B + 1, 0);
+  for (int b = 0; b < B; ++b) {
+    h->bm_chunk_off[(size_t)b] = (int)cptr.size();
+    int64_t e = start[(size_t)b];
+    const int64_t end = start[(size_t)b + 1];
+    while (e < end) {
+      cptr.push_back((int)e);
+      int64_t f = std::min(end, e + BM_CHUNK);
+      while (f < end && erow[(size_t)f] == erow[(size_t)f - 1]) ++f;  // a row never straddles two chunks
+      e = f;
+    }
+    cptr.push_back((int)end);  // closes the last chunk of the block (a block's chunk table has nchunks + 1 entries)
+  }
+  h->bm_chunk_off[(size_t)B] = (int)cptr.size();
+  CUDA_TRY(h, cudaMalloc((void**)&h->bm_col, (size_t)nnz * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->bm_row, (size_t)nnz * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->bm_val, (size_t)nnz * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->bm_chunk, cptr.size() * sizeof(int)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->bm_mask, (size_t)nrows * sizeof(unsigned)));
+  CUDA_TRY(h, cudaMemcpy(h->bm_col, ecol.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->bm_row, erow.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->bm_val, ev.data(), (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->bm_chunk, cptr.data(), cptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->bm_mask, mask.data(), (size_t)nrows * sizeof(unsigned), cudaMemcpyHostToDevice));
+  h->bm_B = B;
+  return MANISDP_OK;
+}
+
 static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, const uint64_t* ir, const double* pr,
                                int64_t ncols, int64_t nrows_global) {
   // The column lists of C are exactly the row lists the kernels need: out(j,:) = sum_i C(i,j) Y(i,:) is the
@@ -212,6 +283,15 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
     h->C_remote_fraction = nnz ? (double)remote / (double)nnz : 0.0;
     const char* eg = getenv("MANISDP_PEER_GATHER_MAX");
     if (eg) h->peer_gather_max_remote = atof(eg);
+  }
+  {
+    const char* ebm = getenv("MANISDP_SPMM_BM");
+    if (ebm) h->bm_mode = atoi(ebm);
+    // auto: single GPU, no locality, operand at the nominal width p = 64 at least twice the L2 target
+    const bool want = h->world == 1 && nnz > 0 &&
+                      (h->bm_mode == 2 || (h->bm_mode == 1 && h->C_far_fraction > 0.5 &&
+                                           ncols * 512 >= 4 * h->spmm_l2_target));
+    if (want) MSDP_TRY(build_block_major(h, rp, ci, pr + base, ncols));
   }
   out.nrows = ncols;
   out.nnz = (int64_t)nnz;
@@ -299,6 +379,9 @@ static void free_all(manisdp_handle* h) {
   if (h->spmm_bptr) cudaFree(h->spmm_bptr);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->owner_bptr) cudaFree(h->owner_bptr);
+  void* bm[] = {h->bm_col, h->bm_row, h->bm_chunk, h->bm_val, h->bm_mask, h->bm_part};
+  for (void* q : bm)
+    if (q) cudaFree(q);
   if (h->C.col) cudaFree(h->C.col);
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);

@@ -130,7 +130,17 @@ struct manisdp_handle {
   int* spmm_bptr = nullptr;
   size_t spmm_bptr_cap = 0;
   int spmm_use_bulk = 1;               // 1: cp.async.bulk gather kernel for ld >= 32 ; 0: register gathers only
-  int spmm_narrow = 1;                 // 1: k_spmm_narrow for ld <= 32 (MANISDP_SPMM_NARROW=0: generic kernel everywhere)
+  // block-major entry stream of C (spmm.cu: launch_bm) for the product on large graphs without locality: entries
+  // stored column block by column block as (col, val, row), row-aligned chunks per warp, per-block partial rows
+  int bm_mode = 0;                     // MANISDP_SPMM_BM: 0 off, 1 auto (no locality, operand >= 2x L2), 2 always
+  int bm_B = 0;                        // number of column blocks (0: format not built)
+  int *bm_col = nullptr, *bm_row = nullptr, *bm_chunk = nullptr;
+  double* bm_val = nullptr;
+  unsigned* bm_mask = nullptr;         // per row: bit b set iff the row has entries in block b
+  std::vector<int> bm_chunk_off;       // first chunk of each block (B + 1)
+  double* bm_part = nullptr;           // B x nloc x ld partial rows
+  size_t bm_part_cap = 0;
+  int spmm_narrow = 1;                // 1: k_spmm_narrow for ld <= 32 (MANISDP_SPMM_NARROW=0: generic kernel everywhere)
   int spmm_block_mode = 0;             // 0 never (default), 1 auto (only for matrices without locality), 2 always
   int64_t spmm_l2_target = 64ll << 20; // bytes of operand rows per column block
   int C_sorted = 0;                    // rows of C are column-sorted

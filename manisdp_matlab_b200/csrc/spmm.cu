@@ -661,6 +661,139 @@ static int launch_bulk(manisdp_handle* h, const SpmmArgs& a) {
   return MANISDP_OK;
 }
 
+// ---- block-major product (32 < ld <= 64, single GPU, graphs without locality) ----------------------------------------
+// The operand of the bench instance (n = 1e6, p = 64: 512 MB) is 4x the L2 and the graph has no locality, so the row
+// kernels above re-read it ~10x from HBM.  Here the entries are stored column block by column block (api.cu:
+// build_block_major) and one launch per block streams them: a warp takes a row-aligned chunk of ~224 consecutive
+// entries = hundreds of independent gathers from a block that stays in L2, accumulates while the row stays the same and
+// stores the partial row of (block, row) into the block's own buffer when the row changes (no read inside a pass, so
+// no dependent load).  k_bm_finish then adds the partial rows a row really has (bit mask per row) and applies the
+// usual fused epilogue and reductions.  Measured in tools/spmm_blockmajor_lab.cu (profiles/r1_spmm_blockmajor_lab.txt):
+// 2.86 ms against 3.44-3.88 ms for the single pass; per-pass times sit on the L2 gather rate (13-19 TB/s).
+// STATUS (end of round 1): correct (tests/test_gpu_maxcut.py forces it with MANISDP_SPMM_BM=2) but OPT-IN -- inside the
+// product the pass kernel runs at 0.84 ms against 0.62 ms in the lab and the epilogue pass costs 0.66 ms, 4.09 ms per
+// product against 3.69 ms for k_spmm (profiles/r1_blockmajor_product_ab.txt); the default stays the row kernel until
+// the pass reaches the lab's rate.
+// Entry order within a row is unchanged; only the association of the sum changes (per-block partial sums).
+#define BM_U 8
+template <int EPI>
+__global__ void __launch_bounds__(MSDP_THREADS, 3)
+    k_bm_pass(const SpmmArgs a, const int* __restrict__ ecol, const double* __restrict__ eval_,
+              const int* __restrict__ erow, const int* __restrict__ chunk_ptr, int nchunks, double* __restrict__ part) {
+  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  const SpmmPtrs p = select_ptrs(a);
+  const double* __restrict__ Ug = p.Ug;
+  const int ld = a.ld;
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < ld / 2;
+  const int nw = gridDim.x * (MSDP_THREADS / 32);
+  for (int ch = blockIdx.x * (MSDP_THREADS / 32) + (threadIdx.x >> 5); ch < nchunks; ch += nw) {
+    const int e0 = __ldg(chunk_ptr + ch), e1 = __ldg(chunk_ptr + ch + 1);
+    int cur = -1, prev_last = -1;
+    double2 acc = make_double2(0.0, 0.0);
+    int c = 0, r = -1;
+    double w = 0.0;
+    if (e0 + lane < e1) {
+      c = __ldg(ecol + e0 + lane);
+      w = __ldg(eval_ + e0 + lane);
+      r = __ldg(erow + e0 + lane);
+    }
+    for (int base = e0; base < e1; base += 32) {
+      int cn = 0, rn = -1;
+      double wn = 0.0;
+      if (base + 32 + lane < e1) {  // next group's entries before this group's gathers
+        cn = __ldg(ecol + base + 32 + lane);
+        wn = __ldg(eval_ + base + 32 + lane);
+        rn = __ldg(erow + base + 32 + lane);
+      }
+      const int cnt = min(32, e1 - base);
+      int rprev = __shfl_up_sync(0xffffffffu, r, 1);
+      if (lane == 0) rprev = prev_last;
+      const unsigned chg = __ballot_sync(0xffffffffu, lane < cnt && r != rprev);  // bit k: entry k starts a new row
+      prev_last = __shfl_sync(0xffffffffu, r, cnt - 1);
+      // lanes past cnt hold (column 0, weight 0): the count is rounded up to the unroll width
+      const int cnt_pad = min(32, (cnt + BM_U - 1) / BM_U * BM_U);
+      for (int k = 0; k < cnt_pad; k += BM_U) {
+        double2 u[BM_U];
+#pragma unroll
+        for (int s = 0; s < BM_U; ++s) {
+          const int cj = __shfl_sync(0xffffffffu, c, k + s);
+          u[s] = act ? ldg2(Ug + (size_t)cj * ld + 2 * lane) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int s = 0; s < BM_U; ++s) {
+          if ((chg >> (k + s)) & 1u) {  // warp-uniform
+            if (cur >= 0 && act) st2(part + (size_t)cur * ld + 2 * lane, acc);
+            cur = __shfl_sync(0xffffffffu, r, k + s);
+            acc = make_double2(0.0, 0.0);
+          }
+          const double ws = __shfl_sync(0xffffffffu, w, k + s);
+          acc.x = fma(ws, u[s].x, acc.x);
+          acc.y = fma(ws, u[s].y, acc.y);
+        }
+      }
+      c = cn;
+      w = wn;
+      r = rn;
+    }
+    if (cur >= 0 && act) st2(part + (size_t)cur * ld + 2 * lane, acc);
+  }
+}
+
+// out(row) = epilogue( sum over the blocks b with bit b of mask[row] of part[b][row] ), + the reductions / scalar tail
+template <int EPI>
+__global__ void __launch_bounds__(MSDP_THREADS)
+    k_bm_finish(const SpmmArgs a, const double* __restrict__ part, const unsigned* __restrict__ rowmask, int B) {
+  __shared__ double sm[2 * 32];
+  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  const SpmmPtrs p = select_ptrs(a);
+  const int ld = a.ld;
+  const int gl = threadIdx.x & 31;
+  const bool act = gl < ld / 2;
+  const size_t pstride = (size_t)a.nrows * ld;
+  const int64_t ngroups = (int64_t)gridDim.x * (MSDP_THREADS / 32);
+  double q[2] = {0.0, 0.0};
+  for (int64_t row = (int64_t)blockIdx.x * (MSDP_THREADS / 32) + threadIdx.x / 32; row < a.nrows; row += ngroups) {
+    const unsigned m = __ldg(rowmask + row);
+    double2 v[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+      v[b] = (b < B && ((m >> b) & 1u) && act) ? ldcs2(part + (size_t)b * pstride + (size_t)row * ld + 2 * gl)
+                                               : make_double2(0.0, 0.0);
+    double2 acc[1];
+    acc[0] = v[0];
+#pragma unroll
+    for (int b = 1; b < 8; ++b) {
+      acc[0].x += v[b].x;
+      acc[0].y += v[b].y;
+    }
+    row_epilogue<32, 1, EPI>(acc, p, row, ld, gl, 0xffffffffu, q);
+  }
+  spmm_tail<EPI>(a, q, sm);
+}
+
+static bool bm_applies(const manisdp_handle* h, const SpmmArgs& a) {
+  return h->bm_B > 0 && h->bm_part && a.ld > 32 && a.ld <= 64 && !a.sharded && !a.peer_tab &&
+         h->bm_part_cap >= (size_t)h->bm_B * (size_t)a.nrows * (size_t)a.ld;
+}
+
+template <int EPI>
+static int launch_bm(manisdp_handle* h, const SpmmArgs& a) {
+  const int B = h->bm_B;
+  const size_t pstride = (size_t)a.nrows * (size_t)a.ld;
+  const int grid = h->num_sms * 3;
+  for (int b = 0; b < B; ++b) {
+    const int nch = h->bm_chunk_off[(size_t)b + 1] - h->bm_chunk_off[(size_t)b] - 1;
+    if (nch <= 0) continue;
+    k_bm_pass<EPI><<<std::min(grid, (nch + 7) / 8), MSDP_THREADS, 0, h->stream>>>(
+        a, h->bm_col, h->bm_val, h->bm_row, h->bm_chunk + h->bm_chunk_off[(size_t)b], nch, h->bm_part + b * pstride);
+    KERNEL_CHECK(h);
+  }
+  k_bm_finish<EPI><<<rows_grid(h, a.nrows, 32), MSDP_THREADS, 0, h->stream>>>(a, h->bm_part, h->bm_mask, B);
+  KERNEL_CHECK(h);
+  return MANISDP_OK;
+}
+
 template <int GS, int VPL, int EPI>
 static void launch_rows(manisdp_handle* h, const SpmmArgs& a) {
   const int nb = rows_grid(h, a.nrows, GS);
@@ -703,6 +836,7 @@ static int launch_pass(manisdp_handle* h, SpmmArgs a) {
 
 template <int EPI>
 static int launch_spmm(manisdp_handle* h, SpmmArgs a) {
+  if (EPI != EPI_SHIFT && bm_applies(h, a)) return launch_bm<EPI>(h, a);
   MSDP_TRY(msdp_spmm_prepare(h, a.ld));
   const int B = h->spmm_B;
   for (int b = 0; b < B; ++b) {
