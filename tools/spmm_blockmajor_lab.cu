@@ -119,6 +119,83 @@ __global__ void __launch_bounds__(256, MINB) k_bm(const int* __restrict__ ecol, 
   }
 }
 
+// Product-shaped variant of the pass for the next round (runtime row length ld <= 64, as spmm.cu needs it): the
+// gathers stay UNCONDITIONAL -- lanes past ld/2 read column offset 0 of the same row and simply never store -- so the
+// compiler keeps the eight loads in eight register quads back to back (check: cuobjdump -sass shows
+// LDG.E.128.CONSTANT R16, R20, ... with no IMAD.MOV between load and DFMA).  The product kernel of round 1 wrote
+// `u[s] = act ? ldg2(..) : 0`, which routes every load through a temporary and serialises them in ~3 groups.
+template <int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_bm_rt(const int* __restrict__ ecol, const double* __restrict__ eval_,
+                                                     const int* __restrict__ erow, const int* __restrict__ chunk_ptr,
+                                                     int nchunks, const double* __restrict__ Ug, double* __restrict__ part,
+                                                     int ld) {
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < ld / 2;
+  const int lo = act ? 2 * lane : 0;
+  const int nw = gridDim.x * 8;
+  for (int ch = blockIdx.x * 8 + (threadIdx.x >> 5); ch < nchunks; ch += nw) {
+    const int e0 = __ldg(chunk_ptr + ch), e1 = __ldg(chunk_ptr + ch + 1);
+    int cur = -1, prev_last = -1;
+    double2 acc = make_double2(0.0, 0.0);
+    int c = 0, r = -1;
+    double w = 0.0;
+    if (e0 + lane < e1) { c = __ldg(ecol + e0 + lane); w = __ldg(eval_ + e0 + lane); r = __ldg(erow + e0 + lane); }
+    for (int base = e0; base < e1; base += 32) {
+      int cn = 0, rn = -1;
+      double wn = 0.0;
+      if (base + 32 + lane < e1) {
+        cn = __ldg(ecol + base + 32 + lane); wn = __ldg(eval_ + base + 32 + lane); rn = __ldg(erow + base + 32 + lane);
+      }
+      const int cnt = min(32, e1 - base);
+      int rprev = __shfl_up_sync(0xffffffffu, r, 1);
+      if (lane == 0) rprev = prev_last;
+      const unsigned chg = __ballot_sync(0xffffffffu, lane < cnt && r != rprev);
+      prev_last = __shfl_sync(0xffffffffu, r, cnt - 1);
+      const int cnt_pad = min(32, (cnt + U - 1) / U * U);
+      for (int k = 0; k < cnt_pad; k += U) {
+        double2 u[U];
+#pragma unroll
+        for (int s = 0; s < U; ++s) {
+          const int cj = __shfl_sync(0xffffffffu, c, k + s);
+          u[s] = __ldg(reinterpret_cast<const double2*>(Ug + (size_t)cj * ld + lo));
+        }
+#pragma unroll
+        for (int s = 0; s < U; ++s) {
+          if ((chg >> (k + s)) & 1u) {
+            if (cur >= 0 && act) *reinterpret_cast<double2*>(part + (size_t)cur * ld + lo) = acc;
+            cur = __shfl_sync(0xffffffffu, r, k + s);
+            acc = make_double2(0.0, 0.0);
+          }
+          const double ws = __shfl_sync(0xffffffffu, w, k + s);
+          acc.x = fma(ws, u[s].x, acc.x);
+          acc.y = fma(ws, u[s].y, acc.y);
+        }
+      }
+      c = cn; w = wn; r = rn;
+    }
+    if (cur >= 0 && act) *reinterpret_cast<double2*>(part + (size_t)cur * ld + lo) = acc;
+  }
+}
+// (launched by run_rt below; its summing pass reads all B partial rows of every row unconditionally from buffers that
+// were zeroed once -- a (block, row) slot without entries is never written, so it stays zero -- instead of testing a mask)
+template <int NB>
+__global__ void __launch_bounds__(256) k_sum_all(const double* __restrict__ part, long n, int ld, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < ld / 2;
+  const int lo = act ? 2 * lane : 0;
+  const long nw = (long)gridDim.x * 8;
+  const size_t pstride = (size_t)n * ld;
+  for (long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += nw) {
+    double2 v[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) v[b] = __ldcs(reinterpret_cast<const double2*>(part + b * pstride + (size_t)row * ld + lo));
+    double2 acc = v[0];
+#pragma unroll
+    for (int b = 1; b < NB; ++b) { acc.x += v[b].x; acc.y += v[b].y; }
+    if (act) *reinterpret_cast<double2*>(out + (size_t)row * ld + lo) = acc;
+  }
+}
+
 // !RMW variant: pass b stores its partial rows into part[b] (no read, so no dependent load in the pass); this pass adds
 // the partial rows a row actually has (bit b of mask[row]) -- in the product it would carry the projection epilogue
 __global__ void __launch_bounds__(256) k_sum(const double* __restrict__ part, const unsigned* __restrict__ mask, int B,
@@ -194,6 +271,38 @@ static BlockMajor build(const std::vector<int>& rp, const std::vector<int>& ci, 
 
 static void release(BlockMajor& bm) {
   cudaFree(bm.ecol); cudaFree(bm.erow); cudaFree(bm.eval_); cudaFree(bm.chunk_ptr); cudaFree(bm.mask);
+}
+
+// product-shaped variant (runtime ld = 64 here, B = 4): zero the partial buffers once, then passes + k_sum_all
+template <int U, int MINB>
+static float run_rt(const BlockMajor& bm, const double* Ug, double* out, double* part, long n, int sms, int reps,
+                    int* regs, int* occ) {
+  auto kern = k_bm_rt<U, MINB>;
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, kern);
+  *regs = fa.numRegs;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, 256, 0);
+  const int grid = sms * std::max(1, *occ);
+  CK(cudaMemset(part, 0, (size_t)bm.B * n * LD * 8));
+  auto once = [&]() {
+    for (int b = 0; b < bm.B; ++b) {
+      const int nch = bm.chunk_off[b + 1] - bm.chunk_off[b];
+      kern<<<grid, 256>>>(bm.ecol, bm.eval_, bm.erow, bm.chunk_ptr + bm.chunk_off[b], nch, Ug,
+                          part + (size_t)b * n * LD, LD);
+    }
+    k_sum_all<4><<<sms * 8, 256>>>(part, n, LD, out);
+  };
+  once();
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
+  for (int r = 0; r < reps; ++r) once();
+  cudaEventRecord(b);
+  CK(cudaEventSynchronize(b));
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms / reps;
 }
 
 template <int U, int MINB, bool RMW>
@@ -284,6 +393,13 @@ int main(int argc, char** argv) {
            "\"blocks_per_sm\": %d, \"rmw\": %d, \"ms\": %.3f, \"maxdiff\": %.2e}\n", B, chunk, U, minb, regs, occ, rmw, ms, md);
     fflush(stdout);
   };
+  {  // product-shaped variant, B = 4 (reported with rmw = 2)
+    BlockMajor bm = build(rp, ci, va, n, 4, 224);
+    int regs, occ;
+    float ms = run_rt<8, 3>(bm, Ug, o1, part, n, sms, 5, &regs, &occ);
+    report(4, 224, 8, 3, regs, occ, ms, 2);
+    release(bm);
+  }
   const int Bs[] = {2, 3, 4, 6, 8};
   for (int B : Bs) {
     BlockMajor bm = build(rp, ci, va, n, B, 224);
