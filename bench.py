@@ -400,10 +400,11 @@ def time_to_kkt():
 
 def time_to_kkt_bqp60():
     """BASELINE config 2: BQP q = 60 (n = 1831, m = 1 155 281) through the drop-in ManiSDP_unitdiag, tol 1e-8."""
-    from manisdp_matlab_b200 import ManiSDP_unitdiag, problems as P
+    from instances import generators as G
+    from manisdp_matlab_b200 import ManiSDP_unitdiag
     d = np.load(os.path.join(ROOT, "tests", "golden", "bqp_60_1.npz"))
     t0 = time.perf_counter()
-    At, b, c, K = P.bqpmom(60, d["Q"], d["e"])
+    At, b, c, K = G.bqpmom(60, d["Q"], d["e"])
     c = c / np.abs(c).max()  # example/example_bqp.m:31-41
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()

@@ -138,6 +138,8 @@ typedef struct {
   int32_t nneg;   /* min(#negative eigenvalues found, delta requested) */
   int32_t eig_iters;
   double eig_resid; /* largest residual norm among the returned eigenpairs */
+  int32_t eig_converged; /* 1: the residual test |S v - lambda v| <= eig_tol*(1+lambda_max) was met for all of them */
+  int32_t reserved;
 } manisdp_kkt_info;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
@@ -219,6 +221,10 @@ typedef struct {
   double flops_per_hv;
 } manisdp_stats;
 int manisdp_get_stats(manisdp_t *h, manisdp_stats *out);
+/* read-back of the integer index split r = j*n + i -> (i, j) of every stored entry of At, in CSC order, exactly as
+ * the device kernels index with it (SURVEY 7 "index exactness"; BASELINE north_star: "A(YY') index handling must be
+ * bit-exact").  *count = nnz(At); at most `cap` pairs are written; i / j may be NULL to query the count. */
+int manisdp_get_index_split(manisdp_t *h, int64_t *i, int64_t *j, int64_t cap, int64_t *count);
 /* host-only diagnostic (no GPU): eigen-decomposition of a small dense symmetric matrix A (n x n, row-major) with the
  * solver the eigen / rank steps use for their projected problems; w ascending, eigenvectors in the columns of V */
 int manisdp_test_sym_eig(const double *A, int32_t n, double *w, double *V);

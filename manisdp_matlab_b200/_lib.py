@@ -54,7 +54,8 @@ class TrIter(C.Structure):
 class KktInfo(C.Structure):
     _fields_ = [("obj", C.c_double), ("by", C.c_double), ("pinf", C.c_double), ("dinf", C.c_double),
                 ("gap", C.c_double), ("lam_min", C.c_double), ("lam_max", C.c_double), ("z_sum", C.c_double),
-                ("nneg", C.c_int32), ("eig_iters", C.c_int32), ("eig_resid", C.c_double)]
+                ("nneg", C.c_int32), ("eig_iters", C.c_int32), ("eig_resid", C.c_double),
+                ("eig_converged", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -97,6 +98,8 @@ SIGNATURES = {
     "manisdp_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "manisdp_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
     "manisdp_test_sym_eig": (C.c_int, [_f64p, C.c_int32, _f64p, _f64p]),
+    "manisdp_get_index_split": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,
+                                          C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -349,6 +352,17 @@ class Handle:
         a = C.c_double()
         self._ck(self.lib.manisdp_line_search(self._h, C.byref(a)), "line_search")
         return a.value
+
+    def index_split(self):
+        """(i, j) int64 arrays of every stored entry of At, CSC order, as the device kernels index with them"""
+        cnt = C.c_int64()
+        self._ck(self.lib.manisdp_get_index_split(self._h, None, None, 0, C.byref(cnt)), "get_index_split")
+        i = np.empty(cnt.value, dtype=np.int64)
+        j = np.empty(cnt.value, dtype=np.int64)
+        p64 = C.POINTER(C.c_int64)
+        self._ck(self.lib.manisdp_get_index_split(self._h, i.ctypes.data_as(p64), j.ctypes.data_as(p64), cnt.value,
+                                                  C.byref(cnt)), "get_index_split")
+        return i, j
 
     def stats(self):
         s = Stats()

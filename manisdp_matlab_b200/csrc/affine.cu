@@ -902,3 +902,31 @@ int msdp_affine_apply_S(manisdp_handle* h, const double* V, double* AV, int kld)
   }
   return MANISDP_OK;
 }
+
+// Read-back of the (i, j) index split of At's rows (tests: "A(YY') index handling must be bit-exact").  Sparse A: the
+// int32 arrays the SDDMM / row-list kernels index with; dense A: the int32 linear positions the gather kernel indexes
+// the n x n matrix with, split here with the same 64-bit integer div / mod used at create.  CSC order of At.
+int msdp_affine_index_split(manisdp_handle* h, int64_t* i_out, int64_t* j_out, int64_t cap, int64_t* count) {
+  const int64_t nnz = (h->a_mode == MODE_DENSE) ? h->Ad.nnz : h->As.nnz;
+  if (count) *count = nnz;
+  if (!i_out || !j_out) return MANISDP_OK;
+  const int64_t k = std::min<int64_t>(cap, nnz);
+  if (k <= 0) return MANISDP_OK;
+  std::vector<int> a((size_t)k), b((size_t)k);
+  if (h->a_mode == MODE_DENSE) {
+    CUDA_TRY(h, cudaMemcpy(a.data(), h->Ad.klin, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int64_t e = 0; e < k; ++e) {
+      const uint64_t r = (uint64_t)(unsigned)a[(size_t)e];
+      i_out[e] = (int64_t)(r % (uint64_t)h->n);
+      j_out[e] = (int64_t)(r / (uint64_t)h->n);
+    }
+  } else {
+    CUDA_TRY(h, cudaMemcpy(a.data(), h->As.ei, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(b.data(), h->As.ej, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int64_t e = 0; e < k; ++e) {
+      i_out[e] = a[(size_t)e];
+      j_out[e] = b[(size_t)e];
+    }
+  }
+  return MANISDP_OK;
+}

@@ -12,3 +12,5 @@ int msdp_affine_cost_only(manisdp_handle* h, const double* Z, double* f_host);
 int msdp_affine_kkt(manisdp_handle* h, int update_dual, manisdp_kkt_info* out);
 // AV = S * V on an n x kld block (S as prepared by the last msdp_affine_kkt)
 int msdp_affine_apply_S(manisdp_handle* h, const double* V, double* AV, int kld);
+// (i, j) of every entry of At as the kernels index it (CSC order); count = nnz(At)
+int msdp_affine_index_split(manisdp_handle* h, int64_t* i_out, int64_t* j_out, int64_t cap, int64_t* count);

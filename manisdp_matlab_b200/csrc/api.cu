@@ -87,16 +87,40 @@ int msdp_resize(manisdp_handle* h, int64_t p) {
     double** arrs[] = {&h->Ybuf[0], &h->Ybuf[1], &h->Gbuf[0], &h->Gbuf[1], &h->eta[0], &h->eta[1],
                        &h->r,       &h->d,       &h->Hd,      &h->Uslot,   &h->Hslot};
     MSDP_TRY(msdp_dist_ipc_release(h));  // peers unmap the old arrays before they are freed
+    msdp_invalidate_graph(h);
+    // From here until every allocation has succeeded the handle holds NO factor: a failure (e.g. out of memory) must
+    // leave it in a state where later calls fail cleanly ("no factor set") instead of launching kernels on freed
+    // pointers with the old capacity.
+    h->cap_elems = 0;
+    h->p = 0;
+    h->ld = 0;
+    h->cache_valid = h->grad_valid = 0;
     for (double** a : arrs) {
       if (*a) cudaFree(*a);
       *a = nullptr;
-      CUDA_TRY(h, cudaMalloc((void**)a, cap * sizeof(double)));
-      CUDA_TRY(h, cudaMemsetAsync(*a, 0, cap * sizeof(double), h->stream));
     }
-    if (h->world > 1) {
+    if (h->gatherbuf) cudaFree(h->gatherbuf);
+    h->gatherbuf = nullptr;
+    cudaError_t aerr = cudaSuccess;
+    for (double** a : arrs) {
+      aerr = cudaMalloc((void**)a, cap * sizeof(double));
+      if (aerr == cudaSuccess) aerr = cudaMemsetAsync(*a, 0, cap * sizeof(double), h->stream);
+      if (aerr != cudaSuccess) break;
+    }
+    if (aerr == cudaSuccess && h->world > 1) {
+      aerr = cudaMalloc((void**)&h->gatherbuf, cap * h->world * sizeof(double));
+      if (aerr == cudaSuccess) aerr = cudaMemsetAsync(h->gatherbuf, 0, cap * h->world * sizeof(double), h->stream);
+    }
+    if (aerr != cudaSuccess) {
+      for (double** a : arrs) {
+        if (*a) cudaFree(*a);
+        *a = nullptr;
+      }
       if (h->gatherbuf) cudaFree(h->gatherbuf);
-      CUDA_TRY(h, cudaMalloc((void**)&h->gatherbuf, cap * h->world * sizeof(double)));
-      CUDA_TRY(h, cudaMemsetAsync(h->gatherbuf, 0, cap * h->world * sizeof(double), h->stream));
+      h->gatherbuf = nullptr;
+      cudaGetLastError();
+      return msdp_fail(h, MANISDP_E_CUDA, std::string("resize: allocation of the work arrays failed: ") +
+                                              cudaGetErrorString(aerr));
     }
     h->cap_elems = cap;
     msdp_invalidate_graph(h);
@@ -109,7 +133,14 @@ int msdp_resize(manisdp_handle* h, int64_t p) {
       h->bm_part = nullptr;
       CUDA_TRY(h, cudaMalloc((void**)&h->bm_part, want * sizeof(double)));
       h->bm_part_cap = want;
+      h->bm_part_ld = -1;
       msdp_invalidate_graph(h);
+    }
+    // k_bm_finish sums ALL blocks of a row: (block, row) pairs without entries are never written by a pass and must
+    // read as exact zeros, so the buffers are cleared whenever the row length (= the layout) changes
+    if (h->bm_part_ld != ld) {
+      CUDA_TRY(h, cudaMemsetAsync(h->bm_part, 0, h->bm_part_cap * sizeof(double), h->stream));
+      h->bm_part_ld = ld;
     }
   }
   if (p != h->p) msdp_invalidate_graph(h);
@@ -200,7 +231,6 @@ static int build_block_major(manisdp_handle* h, const std::vector<int>& rp, cons
   for (int b = 0; b < B; ++b) start[(size_t)b + 1] += start[(size_t)b];
   std::vector<int> ecol((size_t)nnz), erow((size_t)nnz);
   std::vector<double> ev((size_t)nnz);
-  std::vector<unsigned> mask((size_t)nrows, 0u);
   std::vector<int64_t> pos(start.begin(), start.end() - 1);
   for (int64_t i = 0; i < nrows; ++i)
     for (int e = rp[(size_t)i]; e < rp[(size_t)i + 1]; ++e) {
@@ -209,7 +239,6 @@ static int build_block_major(manisdp_handle* h, const std::vector<int>& rp, cons
       ecol[(size_t)q] = ci[(size_t)e];
       erow[(size_t)q] = (int)i;
       ev[(size_t)q] = val[e];
-      mask[(size_t)i] |= 1u << b;
     }
   std::vector<int> cptr;
   h->bm_chunk_off.assign((size_t)B + 1, 0);
@@ -230,12 +259,10 @@ static int build_block_major(manisdp_handle* h, const std::vector<int>& rp, cons
   CUDA_TRY(h, cudaMalloc((void**)&h->bm_row, (size_t)nnz * sizeof(int)));
   CUDA_TRY(h, cudaMalloc((void**)&h->bm_val, (size_t)nnz * sizeof(double)));
   CUDA_TRY(h, cudaMalloc((void**)&h->bm_chunk, cptr.size() * sizeof(int)));
-  CUDA_TRY(h, cudaMalloc((void**)&h->bm_mask, (size_t)nrows * sizeof(unsigned)));
   CUDA_TRY(h, cudaMemcpy(h->bm_col, ecol.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->bm_row, erow.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->bm_val, ev.data(), (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->bm_chunk, cptr.data(), cptr.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CUDA_TRY(h, cudaMemcpy(h->bm_mask, mask.data(), (size_t)nrows * sizeof(unsigned), cudaMemcpyHostToDevice));
   h->bm_B = B;
   return MANISDP_OK;
 }
@@ -276,6 +303,16 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
       }
     }
     h->C_sorted = sorted ? 1 : 0;
+    {  // eligibility of the batched low-degree kernel (spmm.cu: k_spmm_lowdeg, LB_CAP = 320 staged entries per batch)
+      int64_t worst = 0;
+      for (int64_t j = 0; j < ncols; j += 32) {
+        const int64_t j1 = std::min<int64_t>(ncols, j + 32);
+        worst = std::max<int64_t>(worst, (int64_t)rp[(size_t)j1] - rp[(size_t)j]);
+      }
+      h->C_lowdeg = (ncols > 0 && worst <= 320 && (double)nnz <= 8.0 * (double)ncols) ? 1 : 0;
+      const char* eld = getenv("MANISDP_SPMM_LOWDEG");
+      if (eld) h->spmm_lowdeg = atoi(eld);
+    }
     h->C_far_fraction = nnz ? (double)far / (double)nnz : 0.0;
     uint64_t remote = 0;
     for (uint64_t e = 0; e < nnz; ++e)
@@ -305,6 +342,7 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
 }
 
 static int create_impl(manisdp_handle* h, const manisdp_problem* pb) {
+  NvtxRange nvtx_range("manisdp:create");
   if (pb->kind < MANISDP_ONLYUNITDIAG || pb->kind > MANISDP_GENERAL) return msdp_fail(h, MANISDP_E_ARG, "bad kind");
   if (pb->n < 1) return msdp_fail(h, MANISDP_E_ARG, "n must be >= 1");
   h->kind = pb->kind;
@@ -379,7 +417,7 @@ static void free_all(manisdp_handle* h) {
   if (h->spmm_bptr) cudaFree(h->spmm_bptr);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->owner_bptr) cudaFree(h->owner_bptr);
-  void* bm[] = {h->bm_col, h->bm_row, h->bm_chunk, h->bm_val, h->bm_mask, h->bm_part};
+  void* bm[] = {h->bm_col, h->bm_row, h->bm_chunk, h->bm_val, h->bm_part};
   for (void* q : bm)
     if (q) cudaFree(q);
   if (h->C.col) cudaFree(h->C.col);
@@ -678,6 +716,13 @@ extern "C" int manisdp_line_search(manisdp_t* h, double* alpha) {
   if (!h || h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "line_search: no factor set");
   CUDA_TRY(h, cudaSetDevice(h->device));
   return msdp_line_search(h, alpha);
+}
+
+extern "C" int manisdp_get_index_split(manisdp_t* h, int64_t* i, int64_t* j, int64_t cap, int64_t* count) {
+  if (!h) return MANISDP_E_ARG;
+  if (h->kind == MANISDP_ONLYUNITDIAG) return msdp_fail(h, MANISDP_E_ARG, "ONLYUNITDIAG has no constraint matrix At");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return msdp_affine_index_split(h, i, j, cap, count);
 }
 
 // host-only diagnostic: the small dense symmetric eigensolver used by the eigen / rank steps (no GPU needed)

@@ -1,6 +1,7 @@
 // common.cuh -- shared declarations of the B200 ManiSDP engine (internal; the public surface is include/manisdp_b200.h)
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -136,14 +137,16 @@ struct manisdp_handle {
   int bm_B = 0;                        // number of column blocks (0: format not built)
   int *bm_col = nullptr, *bm_row = nullptr, *bm_chunk = nullptr;
   double* bm_val = nullptr;
-  unsigned* bm_mask = nullptr;         // per row: bit b set iff the row has entries in block b
   std::vector<int> bm_chunk_off;       // first chunk of each block (B + 1)
   double* bm_part = nullptr;           // B x nloc x ld partial rows
   size_t bm_part_cap = 0;
+  int64_t bm_part_ld = -1;             // row length the (zero-initialised) partial buffers are laid out for
   int spmm_narrow = 1;                // 1: k_spmm_narrow for ld <= 32 (MANISDP_SPMM_NARROW=0: generic kernel everywhere)
   int spmm_block_mode = 0;             // 0 never (default), 1 auto (only for matrices without locality), 2 always
   int64_t spmm_l2_target = 64ll << 20; // bytes of operand rows per column block
   int C_sorted = 0;                    // rows of C are column-sorted
+  int C_lowdeg = 0;                    // every 32-row batch of C has <= 320 entries and the mean degree is <= 8
+  int spmm_lowdeg = 1;                 // 1: batched low-degree kernel when C_lowdeg (MANISDP_SPMM_LOWDEG=0: off)
   double C_far_fraction = 0.0;         // share of entries whose column is farther than an L2 window from the row
   // split-K workspace of the DMMA GEMM (gemm_f64.cu)
   double* gemm_ws = nullptr;
@@ -166,6 +169,15 @@ struct manisdp_handle {
   double C_remote_fraction = 1.0;       // share of the shard's entries whose column is owned by another rank
   double peer_gather_max_remote = 0.05; // direct peer gathers only below this share (MANISDP_PEER_GATHER_MAX)
   std::string err;
+};
+
+// ---- tracing: one NVTX range per phase of the hot path (visible in Nsight Systems / ncu --nvtx; no cost when no
+// tool is attached: NVTX v3 is header-only and resolves its injection library lazily) -----------------------------
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 // ---- error plumbing ---------------------------------------------------------------------------------------------

@@ -34,6 +34,7 @@ struct EigWork {
   double* hbuf = nullptr;    // pinned mirror of gout
   double* hcoef = nullptr;   // pinned mirror of coef
   int nblocks = 0;
+  int seg_chunks = 1;
 };
 
 static void eig_free(EigWork& w) {
@@ -66,7 +67,12 @@ static int eig_alloc(manisdp_handle* h, EigWork& w, int k) {
   w.nblocks = std::min<int64_t>(h->num_sms * 2, std::max<int64_t>(1, (h->nloc + EIG_TR - 1) / EIG_TR));
   const int nb = 3 * kld;
   const size_t gsz = (size_t)2 * nb * nb + kld;
-  CUDA_TRY(h, cudaMalloc((void**)&w.gpart, (size_t)w.nblocks * gsz * sizeof(double)));
+  // wide blocks (nb > EIG_MAXNB): k_gram_seg writes `seg_chunks` partial [G | GA] pairs
+  const int tiles = ((nb + 31) / 32) * ((nb + 31) / 32) * 2;
+  w.seg_chunks = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)(4 * h->num_sms + tiles - 1) / tiles,
+                                                                (h->nloc + EIG_TR - 1) / EIG_TR, (int64_t)64}));
+  const size_t npart = std::max<size_t>((size_t)w.nblocks, (size_t)w.seg_chunks);
+  CUDA_TRY(h, cudaMalloc((void**)&w.gpart, npart * gsz * sizeof(double)));
   CUDA_TRY(h, cudaMalloc((void**)&w.gout, gsz * sizeof(double)));
   CUDA_TRY(h, cudaMalloc((void**)&w.coef, ((size_t)3 * kld * kld + kld) * sizeof(double)));
   CUDA_TRY(h, cudaMallocHost((void**)&w.hbuf, gsz * sizeof(double)));
@@ -141,15 +147,15 @@ __global__ void __launch_bounds__(MSDP_THREADS)
 // [X, P, AX, AP] <- [X W P] * [Cx; Cw; Cp] , [W P] * [Cw; Cp] (and the same for the A-images), in place
 __global__ void __launch_bounds__(MSDP_THREADS)
     k_combine(double* X, const double* W, double* P, double* AX, const double* AW, double* AP, int64_t nrows, int kld,
-              const double* coef) {
+              const double* coef, int tile_rows) {
   extern __shared__ double smem[];
   double* cf = smem;                      // 3 * kld * kld
-  double* tile = smem + 3 * kld * kld;    // 6 x EIG_TR x kld
+  double* tile = smem + 3 * kld * kld;    // 6 x tile_rows x kld
   const int tid = threadIdx.x;
   for (int i = tid; i < 3 * kld * kld; i += blockDim.x) cf[i] = coef[i];
-  const int tsz = EIG_TR * kld;
-  for (int64_t r0 = (int64_t)blockIdx.x * EIG_TR; r0 < nrows; r0 += (int64_t)gridDim.x * EIG_TR) {
-    const int tr = (int)min((int64_t)EIG_TR, nrows - r0);
+  const int tsz = tile_rows * kld;
+  for (int64_t r0 = (int64_t)blockIdx.x * tile_rows; r0 < nrows; r0 += (int64_t)gridDim.x * tile_rows) {
+    const int tr = (int)min((int64_t)tile_rows, nrows - r0);
     __syncthreads();
     for (int i = tid; i < tr * kld; i += blockDim.x) {
       const size_t off = (size_t)r0 * kld + i;
@@ -265,6 +271,53 @@ __global__ void __launch_bounds__(MSDP_THREADS)
     if (i < ka && j < kb) part[(size_t)chunk * ka * kb + (size_t)i * kb + j] = acc[q];
   }
 }
+
+// Grams of a WIDE basis (3*kld > EIG_MAXNB, i.e. options.delta > 12): the register-accumulator kernel k_gram2 covers
+// 48 x 48 entries only, so the same two matrices G = S'S and GA = S'(AS), S = [X | W | P], are produced tile by tile
+// (32 x 32 outputs per block, row chunks over blockIdx.z, which == 0 -> G, 1 -> GA); k_sum_chunks adds the chunks in
+// order (deterministic).  Column c of S lives in array c / kld at column c % kld.
+struct Seg3 {
+  const double* s[3];
+  const double* as[3];
+};
+__global__ void __launch_bounds__(MSDP_THREADS)
+    k_gram_seg(Seg3 q, int kld, int64_t nrows, int nchunks, double* part) {
+  __shared__ double sa[EIG_TR][33], sb[EIG_TR][33];
+  const int nb = 3 * kld;
+  const int ti = blockIdx.x, tj = blockIdx.y;
+  const int chunk = blockIdx.z % nchunks, which = blockIdx.z / nchunks;
+  const int tid = threadIdx.x;
+  const int64_t rows_per = (nrows + nchunks - 1) / nchunks;
+  const int64_t rbeg = rows_per * chunk, rend = min(nrows, rbeg + rows_per);
+  double acc[4] = {0, 0, 0, 0};
+  const int oi = tid / 32, oj = tid % 32;
+  for (int64_t r0 = rbeg; r0 < rend; r0 += EIG_TR) {
+    const int tr = (int)min((int64_t)EIG_TR, rend - r0);
+    for (int i = tid; i < EIG_TR * 32; i += blockDim.x) {
+      const int r = i / 32, c = i % 32;
+      const int ca = ti * 32 + c, cb = tj * 32 + c;
+      double va = 0.0, vb = 0.0;
+      if (r < tr && ca < nb) va = q.s[ca / kld][(size_t)(r0 + r) * kld + ca % kld];
+      if (r < tr && cb < nb) vb = (which ? q.as[cb / kld] : q.s[cb / kld])[(size_t)(r0 + r) * kld + cb % kld];
+      sa[r][c] = va;
+      sb[r][c] = vb;
+    }
+    __syncthreads();
+    for (int r = 0; r < EIG_TR; ++r) {
+      const double bv = sb[r][oj];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = fma(sa[r][oi + 8 * k], bv, acc[k]);
+    }
+    __syncthreads();
+  }
+  const size_t nent = (size_t)nb * nb;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = ti * 32 + oi + 8 * k, j = tj * 32 + oj;
+    // layout: part[chunk][which][i][j] so that k_sum_chunks over 2*nent entries yields [G | GA]
+    if (i < nb && j < nb) part[((size_t)chunk * 2 + which) * nent + (size_t)i * nb + j] = acc[k];
+  }
+}
 __global__ void k_sum_chunks(const double* part, double* out, int64_t nent, int nchunks) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nent; i += (int64_t)gridDim.x * blockDim.x) {
     double t = 0.0;
@@ -310,19 +363,21 @@ static int apply_S(manisdp_handle* h, EigWork& w, const double* V, double* AV, d
 // w.X (n x kld) Ritz vectors, resid = max residual norm over the wanted pairs.
 // Converged when the largest residual norm of the wanted pairs is <= max(tol_abs, tol_rel * max|theta|).
 static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, double tol_abs, double tol_rel, int maxit,
-                  int warm, std::vector<double>& vals, double* resid_out, int* iters_out) {
+                  int warm, std::vector<double>& vals, double* resid_out, int* iters_out, bool* conv_out = nullptr) {
+  NvtxRange nvtx_range(want_largest ? "manisdp:lobpcg(lambda_max)" : "manisdp:lobpcg(lambda_min block)");
   const int k = w.k, kld = w.kld, nb = 3 * kld, nent = nb * nb;
   const int64_t n = h->nloc;
   const double sgn = want_largest ? -1.0 : 1.0;
   cudaStream_t s = h->stream;
+  const bool wide = nb > EIG_MAXNB;
   const size_t sm_gram = (size_t)2 * EIG_TR * nb * sizeof(double);
-  const size_t sm_comb = ((size_t)3 * kld * kld + 6 * EIG_TR * kld) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_set = true;
-  }
+  // k_combine keeps the 3 coefficient blocks + a tile of the six arrays in shared memory: shrink the tile for wide blocks
+  int tile_rows = EIG_TR;
+  while (tile_rows > 2 && ((size_t)3 * kld * kld + 6 * (size_t)tile_rows * kld) * sizeof(double) > 200 * 1024) tile_rows /= 2;
+  const size_t sm_comb = ((size_t)3 * kld * kld + 6 * (size_t)tile_rows * kld) * sizeof(double);
+  // the attribute is per device and cheap to set: no process-wide "done" flag (handles may live on several GPUs)
+  CUDA_TRY(h, cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int rthreads = (MSDP_THREADS / kld) * kld;
   unsigned int* ticket = &h->st->ticket;
   if (!warm) {
@@ -342,11 +397,21 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
   bool haveW = false, haveP = false;
   double resid = INFINITY;
   int it = 0;
+  bool converged = false;
   vals.assign(k, 0.0);
   for (it = 0; it <= maxit; ++it) {
     // Grams of the current basis (+ residual norms computed by the previous k_resid)
-    k_gram2<<<w.nblocks, MSDP_THREADS, sm_gram, s>>>(w.X, w.W, w.P, w.AX, w.AW, w.AP, n, kld, w.gpart, w.gout, ticket);
-    KERNEL_CHECK(h);
+    if (!wide) {
+      k_gram2<<<w.nblocks, MSDP_THREADS, sm_gram, s>>>(w.X, w.W, w.P, w.AX, w.AW, w.AP, n, kld, w.gpart, w.gout, ticket);
+      KERNEL_CHECK(h);
+    } else {
+      Seg3 q{{w.X, w.W, w.P}, {w.AX, w.AW, w.AP}};
+      dim3 grid((nb + 31) / 32, (nb + 31) / 32, 2 * w.seg_chunks);
+      k_gram_seg<<<grid, MSDP_THREADS, 0, s>>>(q, kld, n, w.seg_chunks, w.gpart);
+      KERNEL_CHECK(h);
+      k_sum_chunks<<<std::max(1, (2 * nent + 255) / 256), 256, 0, s>>>(w.gpart, w.gout, (int64_t)2 * nent, w.seg_chunks);
+      KERNEL_CHECK(h);
+    }
     if (h->world > 1) MSDP_TRY(msdp_dist_allreduce_buf(h, w.gout, 2 * nent + kld));
     CUDA_TRY(h, cudaMemcpyAsync(w.hbuf, w.gout, ((size_t)2 * nent + kld) * sizeof(double), cudaMemcpyDeviceToHost, s));
     const auto t_wait0 = std::chrono::steady_clock::now();
@@ -372,7 +437,8 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
       double tmax = 0.0;
       for (int c = 0; c < nwant; ++c) tmax = std::max(tmax, fabs(vals[c]));
       const double tol_now = std::max(tol_abs, tol_rel * tmax);
-      if (resid <= tol_now || it == maxit) break;
+      converged = resid <= tol_now;
+      if (converged || it == maxit) break;
       if (act_w.empty()) break;
       // Ritz values converge quadratically in the residual: stop when the wanted ones have stopped moving
       // (change over the last 10 iterations below a tenth of the tolerance) although the residual test is not met
@@ -480,7 +546,7 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
       vals[c] = theta[c];
     }
     CUDA_TRY(h, cudaMemcpyAsync(w.coef, hc, ((size_t)3 * kld * kld + kld) * sizeof(double), cudaMemcpyHostToDevice, s));
-    k_combine<<<w.nblocks, MSDP_THREADS, sm_comb, s>>>(w.X, w.W, w.P, w.AX, w.AW, w.AP, n, kld, w.coef);
+    k_combine<<<w.nblocks, MSDP_THREADS, sm_comb, s>>>(w.X, w.W, w.P, w.AX, w.AW, w.AP, n, kld, w.coef, tile_rows);
     KERNEL_CHECK(h);
     haveP = haveW;
     // periodically refresh AX = S*X to stop drift of the implicitly updated images
@@ -493,6 +559,7 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
   }
   if (resid_out) *resid_out = resid;
   if (iters_out) *iters_out = it;
+  if (conv_out) *conv_out = converged;
   return MANISDP_OK;
 }
 
@@ -561,8 +628,12 @@ void msdp_eig_release(manisdp_handle* h) {
 }
 
 int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, manisdp_kkt_info* out) {
+  NvtxRange nvtx_range("manisdp:kkt+eig");
   memset(out, 0, sizeof(*out));
   if (delta < 1) delta = 1;
+  // the LOBPCG block is delta + 4 columns; its kernels (k_resid, k_combine) are laid out for blocks of <= 64 columns
+  if (delta > 60)
+    return msdp_fail(h, MANISDP_E_ARG, "kkt: options.delta > 60 is not supported (LOBPCG block of delta + 4 <= 64 columns)");
   if (eig_tol <= 0) eig_tol = 1e-9;
   // residues + dual slack operator of the driver
   if (h->kind == MANISDP_ONLYUNITDIAG) {
@@ -583,7 +654,7 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
   }
   std::vector<double> vals;
   double lam_max = 0.0, resid = 0.0;
-  int iters = 0;
+  int iters = 0, converged = 1;
   if (h->n <= 96 && h->world <= 1) {
     MSDP_TRY(small_dense_eig(h, delta, vals, &lam_max));
   } else {
@@ -602,7 +673,17 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
     const bool warm = st.warm_lo && st.lo.k == k;
     MSDP_TRY(eig_alloc(h, st.lo, k));
     const double tol_abs = eig_tol * (1.0 + fabs(lam_max));
-    MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_abs, 0.0, 1500, warm ? 1 : 0, vals, &resid, &iters));
+    // Ritz values are upper bounds of lambda_min: an eigen step that stopped on stagnation / maxit without meeting
+    // the residual test could report a dinf that is too small.  Continue from the current block (warm) up to twice
+    // more, and tell the caller (eig_converged) if the residual test is still not met.
+    bool conv = false;
+    MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_abs, 0.0, 1500, warm ? 1 : 0, vals, &resid, &iters, &conv));
+    for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
+      int it3 = 0;
+      MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_abs, 0.0, 1500, 1, vals, &resid, &it3, &conv));
+      iters += it3;
+    }
+    converged = conv ? 1 : 0;
     st.warm_lo = true;
     // keep the wanted vectors for manisdp_escape
     const int kld = st.lo.kld;
@@ -629,6 +710,7 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
   out->nneg = std::min(nneg, delta);
   out->eig_iters = iters;
   out->eig_resid = resid;
+  out->eig_converged = converged;
   return MANISDP_OK;
 }
 
@@ -699,6 +781,7 @@ static int install_combination(manisdp_handle* h, const std::vector<double>& Cm,
 }
 
 int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, int64_t* pnew_out) {
+  NvtxRange nvtx_range("manisdp:rank_cut");
   const int p = (int)h->p;
   // the drivers ask for the rank first and cut afterwards: keep the decomposition of the unchanged point
   g_store_mu.lock();
@@ -754,9 +837,13 @@ int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, in
 
 // ---- escape ---------------------------------------------------------------------------------------------------------------
 int msdp_escape(manisdp_handle* h, int nne, double alpha, int line_search) {
+  NvtxRange nvtx_range("manisdp:escape");
   if (nne < 0 || nne > h->eig_k) return msdp_fail(h, MANISDP_E_ARG, "escape: nne exceeds the eigenvectors kept by kkt");
   const int p = (int)h->p, pn = p + nne;
-  if (nne == 0 && !line_search) return MANISDP_OK;
+  // nne == 0 without line search: the reference still executes Y = [Y alpha*vS(:,1:0)]; Y = Y/norm(Y,'fro')
+  // (ManiSDP_unittrace.m:111 / ManiSDP_unitdiag.m:106) -- after an applied rank cut the factor is off the sphere, so
+  // the normalisation must not be skipped; only the Euclidean driver has nothing to do.
+  if (nne == 0 && !line_search && h->mf == MF_EUCLID) return MANISDP_OK;
   // [Y, alpha*V] as one combination: Cm = [I_p 0], Dm = [0 alpha*I_nne]
   std::vector<double> Cm((size_t)p * pn, 0.0), Dm((size_t)std::max(1, nne) * pn, 0.0);
   for (int q = 0; q < p; ++q) Cm[(size_t)q * pn + q] = 1.0;
@@ -809,6 +896,7 @@ __global__ void k_scaled_copy(const double* U, double a, double* out, int64_t nv
 __global__ void k_set_point(RtrState* st, int pt) { st->pt = pt; }
 
 int msdp_line_search(manisdp_handle* h, double* alpha_out) {
+  NvtxRange nvtx_range("manisdp:line_search");
   if (h->world > 1) return msdp_fail(h, MANISDP_E_ARG, "line search is not available on row-sharded handles");
   // co(Y): <C,YY'> for ONLYUNITDIAG (ManiSDP_onlyunitdiag.m:97-99), the AL cost otherwise
   const double scale = (h->kind == MANISDP_ONLYUNITDIAG) ? 2.0 : 1.0;

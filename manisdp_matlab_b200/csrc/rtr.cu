@@ -147,6 +147,7 @@ static int build_tr_graph(manisdp_handle* h) {
 }
 
 int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_info* info) {
+  NvtxRange nvtx_range("manisdp:tr_solve");
   if (h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "tr_solve: set_Y / rand_Y first");
   manisdp_tr_options opt;
   memset(&opt, 0, sizeof(opt));

@@ -439,6 +439,131 @@ __global__ void __launch_bounds__(MSDP_THREADS, 4) k_spmm_narrow(const SpmmArgs 
   if (last) spmm_tail<EPI>(a, q, sm);
 }
 
+// ---- batched kernel for LOW-DEGREE rows (32 < ld <= 64: one warp per row, one double2 per lane) ------------------------
+// On the toroidal-grid profile (G11/G32/G81 shape: 5 entries per row) 96 % of the algorithmic bytes are plain streams,
+// yet k_spmm reached only 0.40 of the HBM roofline: per row a warp walked a chain of dependent round trips -- row
+// pointers -> (col, val) -> four gathers -> the remaining gather -> epilogue operands -> store -- and nothing of the
+// next row was in flight meanwhile (round-1 VERDICT "what's weak" 4).  Here a warp takes a BATCH of 32 consecutive rows:
+//   * the 33 row pointers and then all (col, val) pairs of the batch (contiguous in the CSR arrays) are fetched with
+//     coalesced loads and staged in shared memory -- two round trips per 32 rows instead of two per row;
+//   * per row, the epilogue operands (Y row, U row, multiplier) and up to LB_GW gathers are issued together, the tail
+//     of a row padded with (own row, weight 0) entries so that the loads stay unconditional (the own row is the line
+//     the epilogue reads anyway);
+//   * Y is read and H written with streaming (evict-first) hints: the L2 is kept for the operand rows, which the
+//     neighbouring rows of the grid re-use.
+// Same entry order and arithmetic as k_spmm, so results are bit-identical to it.  Chosen by launch_pass when every
+// 32-row batch of C has at most LB_CAP entries and the mean degree is <= 8 (api.cu: C_lowdeg).
+#define LB_CAP 320
+#define LB_GW 8
+template <int EPI, bool PEER>
+__global__ void __launch_bounds__(MSDP_THREADS, 3) k_spmm_lowdeg(const SpmmArgs a) {
+  __shared__ double sm[2 * 32];
+  __shared__ int s_col[MSDP_THREADS / 32][LB_CAP];
+  __shared__ double s_val[MSDP_THREADS / 32][LB_CAP];
+  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  const SpmmPtrs p = select_ptrs(a);
+  const int* __restrict__ col = a.col;
+  const double* __restrict__ val = a.val;
+  const double* __restrict__ Ug = p.Ug;
+  const int ld = a.ld;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool act = lane < ld / 2;
+  const int lo = act ? 2 * lane : 0;  // inactive lanes (ld < 64) shadow vector 0 and never store
+  int* sc = s_col[wid];
+  double* sv = s_val[wid];
+  auto operand_row = [&](int c) -> const double* {
+    if (PEER) {
+      const int owner = c / a.rpr;
+      return a.peer_tab[owner] + (size_t)(c - owner * a.rpr) * ld;
+    }
+    return Ug + (size_t)c * ld;
+  };
+  const int64_t nbatches = (a.nrows + 31) / 32;
+  const int64_t nw = (int64_t)gridDim.x * (MSDP_THREADS / 32);
+  double q[2] = {0.0, 0.0};
+  for (int64_t batch = (int64_t)blockIdx.x * (MSDP_THREADS / 32) + wid; batch < nbatches; batch += nw) {
+    const int64_t r0 = batch * 32;
+    const int nr = (int)min((int64_t)32, a.nrows - r0);
+    int e0 = 0, e1 = 0;
+    if (lane < nr) {
+      e0 = __ldg(a.bptr0 + r0 + lane);
+      e1 = __ldg(a.bptr1 + r0 + lane);
+    }
+    const int E0 = __shfl_sync(0xffffffffu, e0, 0);
+    const int E1 = __shfl_sync(0xffffffffu, e1, nr - 1);
+    __syncwarp();  // every lane is done with the previous batch's staged entries
+    for (int t = lane; t < E1 - E0; t += 32) {
+      sc[t] = __ldg(col + E0 + t);
+      sv[t] = __ldg(val + E0 + t);
+    }
+    __syncwarp();
+    for (int r = 0; r < nr; ++r) {
+      const int re0 = __shfl_sync(0xffffffffu, e0, r) - E0, re1 = __shfl_sync(0xffffffffu, e1, r) - E0;
+      const int64_t row = r0 + r;
+      const size_t off = (size_t)row * ld + lo;
+      const int ownc = a.row0 + (int)row;
+      double2 y = make_double2(0.0, 0.0), u = make_double2(0.0, 0.0);
+      double eg = 0.0;
+      if (EPI == EPI_HESS) {
+        y = ldcs2(p.Y + off);
+        u = ld2(p.Uown + off);
+        eg = p.eG[row];
+      } else if (EPI == EPI_COSTGRAD) {
+        y = ld2(p.Uown + off);
+      } else {
+        u = ld2(p.Uown + off);
+        eg = p.eG ? p.eG[row] : 0.0;
+      }
+      double2 acc = make_double2(0.0, 0.0);
+      for (int base = re0; base < re1; base += LB_GW) {
+        double2 g[LB_GW];
+        double w[LB_GW];
+#pragma unroll
+        for (int s = 0; s < LB_GW; ++s) {
+          const bool ok = base + s < re1;
+          const int c = ok ? sc[base + s] : ownc;
+          w[s] = ok ? sv[base + s] : 0.0;
+          g[s] = ldg2(operand_row(c) + lo);
+        }
+#pragma unroll
+        for (int s = 0; s < LB_GW; ++s) {
+          acc.x = fma(w[s], g[s].x, acc.x);
+          acc.y = fma(w[s], g[s].y, acc.y);
+        }
+      }
+      if (EPI == EPI_HESS) {
+        const double dot = warp_sum(act ? y.x * acc.x + y.y * acc.y : 0.0);  // sum(Y.*eH), :129
+        double2 hv;
+        hv.x = acc.x - y.x * dot - u.x * eg;
+        hv.y = acc.y - y.y * dot - u.y * eg;
+        if (act) {
+          stcs2(p.out + off, hv);
+          q[0] += u.x * hv.x + u.y * hv.y;  // <mdelta, Hmdelta>, tCG.m:166
+        }
+      } else if (EPI == EPI_COSTGRAD) {
+        const double dot = warp_sum(act ? y.x * acc.x + y.y * acc.y : 0.0);  // eG(row) = sum(YC.*Y), :119
+        if (lane == 0) {
+          p.eGout[row] = dot;
+          q[0] += dot;
+        }
+        if (act) {
+          double2 gv;
+          gv.x = acc.x - y.x * dot;  // G = YC - Y.*eG, :124
+          gv.y = acc.y - y.y * dot;
+          st2(p.out + off, gv);
+          q[1] += gv.x * gv.x + gv.y * gv.y;
+        }
+      } else if (act) {  // EPI_SHIFT: out = C*V - z.*V
+        double2 o;
+        o.x = acc.x - eg * u.x;
+        o.y = acc.y - eg * u.y;
+        st2(p.out + off, o);
+      }
+    }
+  }
+  spmm_tail<EPI>(a, q, sm);
+}
+
 // ---- bulk-async gather kernel (ld >= 32, one warp per row) ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -647,11 +772,8 @@ int msdp_spmm_prepare(manisdp_handle* h, int ld) {
 template <int VPL, int EPI>
 static int launch_bulk(manisdp_handle* h, const SpmmArgs& a) {
   const size_t smem = (size_t)BULK_WARPS * 2 * a.slots * a.ld * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_spmm_bulk<VPL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_done = true;
-  }
+  // per-device attribute, cheap to set: no process-wide "done" flag (handles may live on several GPUs)
+  CUDA_TRY(h, cudaFuncSetAttribute(k_spmm_bulk<VPL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int64_t rows_per_block = BULK_WARPS;
   int64_t nb = (a.nrows + rows_per_block - 1) / rows_per_block;
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
@@ -686,6 +808,10 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3)
   const int ld = a.ld;
   const int lane = threadIdx.x & 31;
   const bool act = lane < ld / 2;
+  // The gathers are UNCONDITIONAL: a lane past ld/2 (only when ld < 64) reads vector 0 of the same operand row and
+  // never stores.  A predicated `act ? ldg2(..) : 0` made ptxas route every load through a temporary and issue the
+  // eight gathers of a group in ~3 dependent batches (round-1 SASS, profiles/r1_blockmajor_product_ab.txt).
+  const int lo = act ? 2 * lane : 0;
   const int nw = gridDim.x * (MSDP_THREADS / 32);
   for (int ch = blockIdx.x * (MSDP_THREADS / 32) + (threadIdx.x >> 5); ch < nchunks; ch += nw) {
     const int e0 = __ldg(chunk_ptr + ch), e1 = __ldg(chunk_ptr + ch + 1);
@@ -718,7 +844,7 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3)
 #pragma unroll
         for (int s = 0; s < BM_U; ++s) {
           const int cj = __shfl_sync(0xffffffffu, c, k + s);
-          u[s] = act ? ldg2(Ug + (size_t)cj * ld + 2 * lane) : make_double2(0.0, 0.0);
+          u[s] = ldg2(Ug + (size_t)cj * ld + lo);
         }
 #pragma unroll
         for (int s = 0; s < BM_U; ++s) {
@@ -740,30 +866,31 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3)
   }
 }
 
-// out(row) = epilogue( sum over the blocks b with bit b of mask[row] of part[b][row] ), + the reductions / scalar tail
-template <int EPI>
+// out(row) = epilogue( sum over ALL blocks b of part[b][row] ), + the reductions / scalar tail.  The partial buffers
+// are zeroed whenever the row length changes (msdp_resize) and a pass only ever writes the (block, row) pairs that have
+// entries, so a pair without entries reads as an exact 0 -- no per-row mask, no predicated loads: the NB loads of a
+// row (plus the epilogue operands) are in flight together.
+template <int EPI, int NB>
 __global__ void __launch_bounds__(MSDP_THREADS)
-    k_bm_finish(const SpmmArgs a, const double* __restrict__ part, const unsigned* __restrict__ rowmask, int B) {
+    k_bm_finish(const SpmmArgs a, const double* __restrict__ part) {
   __shared__ double sm[2 * 32];
   if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
   const SpmmPtrs p = select_ptrs(a);
   const int ld = a.ld;
   const int gl = threadIdx.x & 31;
   const bool act = gl < ld / 2;
+  const int lo = act ? 2 * gl : 0;
   const size_t pstride = (size_t)a.nrows * ld;
   const int64_t ngroups = (int64_t)gridDim.x * (MSDP_THREADS / 32);
   double q[2] = {0.0, 0.0};
   for (int64_t row = (int64_t)blockIdx.x * (MSDP_THREADS / 32) + threadIdx.x / 32; row < a.nrows; row += ngroups) {
-    const unsigned m = __ldg(rowmask + row);
-    double2 v[8];
+    double2 v[NB];
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
-      v[b] = (b < B && ((m >> b) & 1u) && act) ? ldcs2(part + (size_t)b * pstride + (size_t)row * ld + 2 * gl)
-                                               : make_double2(0.0, 0.0);
+    for (int b = 0; b < NB; ++b) v[b] = ldcs2(part + (size_t)b * pstride + (size_t)row * ld + lo);
     double2 acc[1];
     acc[0] = v[0];
 #pragma unroll
-    for (int b = 1; b < 8; ++b) {
+    for (int b = 1; b < NB; ++b) {
       acc[0].x += v[b].x;
       acc[0].y += v[b].y;
     }
@@ -789,7 +916,16 @@ static int launch_bm(manisdp_handle* h, const SpmmArgs& a) {
         a, h->bm_col, h->bm_val, h->bm_row, h->bm_chunk + h->bm_chunk_off[(size_t)b], nch, h->bm_part + b * pstride);
     KERNEL_CHECK(h);
   }
-  k_bm_finish<EPI><<<rows_grid(h, a.nrows, 32), MSDP_THREADS, 0, h->stream>>>(a, h->bm_part, h->bm_mask, B);
+  const int gf = rows_grid(h, a.nrows, 32);
+  switch (B) {
+    case 2: k_bm_finish<EPI, 2><<<gf, MSDP_THREADS, 0, h->stream>>>(a, h->bm_part); break;
+    case 3: k_bm_finish<EPI, 3><<<gf, MSDP_THREADS, 0, h->stream>>>(a, h->bm_part); break;
+    case 4: k_bm_finish<EPI, 4><<<gf, MSDP_THREADS, 0, h->stream>>>(a, h->bm_part); break;
+    case 5: k_bm_finish<EPI, 5><<<gf, MSDP_THREADS, 0, h->stream>>>(a, h->bm_part); break;
+    case 6: k_bm_finish<EPI, 6><<<gf, MSDP_THREADS, 0, h->stream>>>(a, h->bm_part); break;
+    case 7: k_bm_finish<EPI, 7><<<gf, MSDP_THREADS, 0, h->stream>>>(a, h->bm_part); break;
+    default: k_bm_finish<EPI, 8><<<gf, MSDP_THREADS, 0, h->stream>>>(a, h->bm_part); break;
+  }
   KERNEL_CHECK(h);
   return MANISDP_OK;
 }
@@ -816,6 +952,18 @@ static int launch_pass(manisdp_handle* h, SpmmArgs a) {
   // p = 128), ties at p = 64 and loses below, where four register gathers per group already cover the latency
   const bool bulk = !a.peer_tab && (h->spmm_use_bulk == 2 ? (a.ld >= 32) : (h->spmm_use_bulk == 1 && a.ld >= 96));
   a.slots = std::max(1, std::min(BULK_MAXSLOTS, 4096 / (a.ld * 8)));
+  if (h->spmm_lowdeg && h->C_lowdeg && a.first && a.last && a.bptr0 == h->C.rowptr && a.ld > 32 && a.ld <= 64 &&
+      h->spmm_use_bulk != 2) {
+    a.row0 = (int)h->row_begin;
+    const int nb = (int)std::max<int64_t>(
+        1, std::min<int64_t>((int64_t)h->num_sms * 3, (a.nrows + 32 * (MSDP_THREADS / 32) - 1) / (32 * (MSDP_THREADS / 32))));
+    if (a.peer_tab)
+      k_spmm_lowdeg<EPI, true><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+    else
+      k_spmm_lowdeg<EPI, false><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+    KERNEL_CHECK(h);
+    return MANISDP_OK;
+  }
   if (bulk) {
     const int vpl = row_geom(a.ld).vpl;
     if (vpl == 1)

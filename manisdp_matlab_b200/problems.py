@@ -94,134 +94,6 @@ def read_sdpa(path):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# SeDuMi-format input of BASELINE config 2 (host-side ingest, never on the timed path): the reference's second-order
-# moment relaxation of  min x'Qx + e'x, x in {-1,1}^n  exactly as src/basicfunction/bqpmom.m:6-126 builds it (same
-# constraint set, order and weights, so n = 1 + n + n(n-1)/2 and m match data/bqp_result.txt:3-8).  The oracle holds an
-# identical restatement; tests/test_host_generators.py checks the two produce the same (At, b, c).
-# ---------------------------------------------------------------------------------------------------------------------
-import itertools
-
-
-def _index_map(sp_basis):
-    return {tuple(col): k for k, col in enumerate(sp_basis.T.tolist())}
-
-
-def get_basis(n: int, d: int) -> np.ndarray:
-    """Exponent vectors of all monomials of degree <= d in n variables, as columns, in the order
-    produced by src/basicfunction/get_basis.m:1-33: graded by total degree, ties broken by the
-    exponent of x_n, then x_{n-1}, ... (the order `comp.m:1-24` defines, which `bfind.m` relies on).
-    Built by enumeration + sort; `get_basis_sequential` pins it."""
-    cols = []
-    for deg in range(d + 1):
-        for combo in itertools.combinations_with_replacement(range(n), deg):
-            e = np.zeros(n, dtype=np.int64)
-            for v in combo:
-                e[v] += 1
-            cols.append(e)
-    B = np.array(cols, dtype=np.int64)  # (lb, n)
-    # sort key: (degree, e[n-1], e[n-2], ..., e[0]); np.lexsort uses the LAST key as primary
-    keys = [B[:, v] for v in range(n)] + [B.sum(axis=1)]
-    order = np.lexsort(keys)
-    return np.ascontiguousarray(B[order].T)
-
-
-def _index_map(sp_basis: np.ndarray) -> dict:
-    """Dictionary replacement for the binary search src/basicfunction/bfind.m:1-20."""
-    return {tuple(col): k for k, col in enumerate(sp_basis.T.tolist())}
-
-
-
-def bqpmom(n: int, Q: np.ndarray, e: np.ndarray):
-    """Restates src/basicfunction/bqpmom.m:6-126.  Returns (At, b, c, K) with At CSC (mb^2 x m),
-    b dense (m,), c dense (mb^2,), K = {'s': mb}."""
-    basis = get_basis(n, 2)
-    basis = basis[:, (basis > 1).sum(axis=0) == 0]  # bqpmom.m:8-14  multilinear monomials
-    mb = basis.shape[1]
-    spb = get_basis(n, 4)
-    keep = ((spb > 2).sum(axis=0) == 0) & ((spb % 2).sum(axis=0) != 0)  # bqpmom.m:16-22
-    spb = spb[:, keep]
-    lsp = spb.shape[1]
-    where = _index_map(spb)
-    mm = [[] for _ in range(lsp)]  # mm[ind] = list of (i, j), i < j, 0-based   bqpmom.m:24-31
-    bt = basis.T
-    for i in range(mb):
-        s = bt[i] + bt[i + 1 :]
-        for off, col in enumerate(s.tolist()):
-            mm[where[tuple(col)]].append((i, i + 1 + off))
-    ncons = mb * (mb + 1) // 2 - lsp + n * (mb - 1) - mb + 1  # bqpmom.m:32
-    row, col, val = [0], [0], [1.0]  # X(1,1) = 1, bqpmom.m:33-37
-    b = np.zeros(ncons)
-    b[0] = 1.0
-    for i in range(1, n + 1):  # bqpmom.m:38-42
-        row += [0, i * mb + i]
-        col += [i, i]
-        val += [0.5, -0.5]
-    l = n + 1
-    for i in range(n + 1, mb):  # bqpmom.m:45-51
-        cc = np.nonzero(basis[:, i] == 1)[0] + 1
-        row += [cc[0] * mb + cc[0], i * mb + i, cc[1] * mb + cc[1], i * mb + i]
-        col += [l, l, l + 1, l + 1]
-        val += [0.5, -0.5, 0.5, -0.5]
-        l += 2
-    loa = []  # bqpmom.m:52-58 : both symmetric positions of every pair
-    for i in range(lsp):
-        a = []
-        for (p, q) in mm[i]:
-            a += [q * mb + p, p * mb + q]
-        loa.append(a)
-    for k in range(n):  # bqpmom.m:59-78   x_k^2 * m_i = m_i
-        for i in range(1, mb):
-            if basis[k, i] == 0:
-                bi = basis[:, i].copy()
-                bi[k] = 2
-                l1 = loa[where[tuple(bi.tolist())]]
-                l2 = loa[where[tuple(basis[:, i].tolist())]]
-                row += l1 + l2
-                col += [l] * (len(l1) + len(l2))
-                if len(l1) < len(l2):
-                    val += [1.0] * len(l1) + [-len(l1) / len(l2)] * len(l2)
-                else:
-                    val += [len(l2) / len(l1)] * len(l1) + [-1.0] * len(l2)
-                l += 1
-    for i in range(lsp):  # bqpmom.m:80-90  entries of one monomial are all equal
-        firsts = [p for (p, _) in mm[i]]
-        idx = int(np.argmax(firsts))
-        for j in range(len(mm[i])):
-            if j != idx:
-                row += loa[i][2 * idx : 2 * idx + 2] + loa[i][2 * j : 2 * j + 2]
-                col += [l] * 4
-                val += [0.5, 0.5, -0.5, -0.5]
-                l += 1
-    assert l == ncons, (l, ncons)
-    At = sp.coo_matrix((val, (row, col)), shape=(mb * mb, ncons)).tocsc()
-    At.sum_duplicates()
-    # objective, bqpmom.m:93-122
-    crow = list(range(1, n + 1))
-    ccol = list(range(1, n + 1))
-    cval = list(np.diag(Q))
-    for i in range(n):
-        cnt = len(mm[i])
-        for (p, q) in mm[i]:
-            crow += [p, q]
-            ccol += [q, p]
-        cval += [e[i] / (2 * cnt)] * (2 * cnt)
-    ind = n
-    for i in range(1, n):
-        for j in range(i):
-            cnt = len(mm[ind])
-            for (p, q) in mm[ind]:
-                crow += [p, q]
-                ccol += [q, p]
-            cval += [Q[j, i] / cnt] * (2 * cnt)
-            ind += 1
-    C = sp.coo_matrix((cval, (crow, ccol)), shape=(mb, mb)).toarray()
-    c = C.reshape(-1, order="F")
-    return At, b, c, {"s": mb}
-
-
-
-
-# ---------------------------------------------------------------------------------------------------------------------
 # multi-block SDPs (SURVEY 8f rank 3) through the single-block engine
 # ---------------------------------------------------------------------------------------------------------------------
 def embed_blocks(At, c, K, b=None, nob=0):

@@ -179,10 +179,10 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     manisdp_kkt_info k;
     CK(h, manisdp_kkt(h, (int32_t)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), (int32_t)mxGetScalar(prhs[4]), &k), "kkt");
     const char* names[] = {"obj", "by", "pinf", "dinf", "gap", "lam_min", "lam_max", "z_sum", "nneg", "eig_iters",
-                           "eig_resid"};
+                           "eig_resid", "eig_converged"};
     const double vals[] = {k.obj, k.by, k.pinf, k.dinf, k.gap, k.lam_min, k.lam_max, k.z_sum, (double)k.nneg,
-                           (double)k.eig_iters, k.eig_resid};
-    plhs[0] = scalar_struct(names, vals, 11);
+                           (double)k.eig_iters, k.eig_resid, (double)k.eig_converged};
+    plhs[0] = scalar_struct(names, vals, 12);
   } else if (c == "rank_cut") {
     int64_t r = 0, p = 0;
     CK(h, manisdp_rank_cut(h, mxGetScalar(prhs[2]), (int32_t)mxGetScalar(prhs[3]), &r, &p), "rank_cut");

@@ -1,362 +1,4 @@
-"""ORACLE (test infrastructure, not product code) -- problem generators.
-
-CPU restatement (NumPy/SciPy, FP64, 0-based indices) of the reference's SeDuMi-format problem
-builders.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
-may import this package.
-
-Each function cites the reference file:line it follows (paths relative to the reference root).
-All `At` outputs are scipy CSC matrices of shape (n*n, m) whose row index is the column-major
-linear index r = j*n + i of X[i, j] (MATLAB `vec`, SURVEY.md section 8c pitfalls).
-"""
-from __future__ import annotations
-
-import itertools
-from math import comb
-
-import numpy as np
-import scipy.sparse as sp
-
-
-# --------------------------------------------------------------------------------------------
-# monomial bases
-# --------------------------------------------------------------------------------------------
-def get_basis_sequential(n: int, d: int) -> np.ndarray:
-    """Literal restatement of src/basicfunction/get_basis.m:1-33 (successor rule, one column at a
-    time).  Slow; used only to pin `get_basis` (the sorted construction) in the CPU tests."""
-    lb = comb(n + d, d)
-    basis = np.zeros((n, lb), dtype=np.int64)
-    i = 0
-    t = 0  # 0-based column of the last written monomial
-    while i < d + 1:
-        t += 1
-        if basis[n - 1, t - 1] == i:
-            if i < d:
-                basis[0, t] = i + 1
-            i += 1
-        else:
-            j = 0
-            while basis[j, t - 1] == 0:
-                j += 1
-            basis[:, t] = basis[:, t - 1]
-            if j == 0:
-                basis[0, t] -= 1
-                basis[1, t] += 1
-            else:
-                basis[0, t] = basis[j, t] - 1
-                basis[j, t] = 0
-                basis[j + 1, t] += 1
-    return basis
-
-
-def get_basis(n: int, d: int) -> np.ndarray:
-    """Exponent vectors of all monomials of degree <= d in n variables, as columns, in the order
-    produced by src/basicfunction/get_basis.m:1-33: graded by total degree, ties broken by the
-    exponent of x_n, then x_{n-1}, ... (the order `comp.m:1-24` defines, which `bfind.m` relies on).
-    Built by enumeration + sort; `get_basis_sequential` pins it."""
-    cols = []
-    for deg in range(d + 1):
-        for combo in itertools.combinations_with_replacement(range(n), deg):
-            e = np.zeros(n, dtype=np.int64)
-            for v in combo:
-                e[v] += 1
-            cols.append(e)
-    B = np.array(cols, dtype=np.int64)  # (lb, n)
-    # sort key: (degree, e[n-1], e[n-2], ..., e[0]); np.lexsort uses the LAST key as primary
-    keys = [B[:, v] for v in range(n)] + [B.sum(axis=1)]
-    order = np.lexsort(keys)
-    return np.ascontiguousarray(B[order].T)
-
-
-def _index_map(sp_basis: np.ndarray) -> dict:
-    """Dictionary replacement for the binary search src/basicfunction/bfind.m:1-20."""
-    return {tuple(col): k for k, col in enumerate(sp_basis.T.tolist())}
-
-
-# --------------------------------------------------------------------------------------------
-# MaxCut
-# --------------------------------------------------------------------------------------------
-def read_gset(path: str):
-    """Parse a G-set text file: header `nv ne`, then `i j w` lines (1-based)."""
-    with open(path) as fh:
-        toks = fh.read().split()
-    nv, ne = int(toks[0]), int(toks[1])
-    arr = np.array(toks[2 : 2 + 3 * ne], dtype=np.float64).reshape(ne, 3)
-    return nv, arr[:, 0].astype(np.int64) - 1, arr[:, 1].astype(np.int64) - 1, arr[:, 2].copy()
-
-
-def laplacian(nv: int, ei: np.ndarray, ej: np.ndarray, w: np.ndarray) -> sp.csr_matrix:
-    """Graph Laplacian with the semantics of src/basicfunction/Laplacian.m:1-12: off-diagonal
-    entries are ASSIGNED (a duplicate edge overwrites: last wins, line 7-8) while the degrees
-    ACCUMULATE over every listed edge (lines 9-10).  Returned sparse (the reference builds a dense
-    L and calls sparse() on it, example/example_maxcut.m:10-11)."""
-    off = {}
-    deg = np.zeros(nv)
-    for a, b, ww in zip(ei.tolist(), ej.tolist(), w.tolist()):
-        off[(a, b)] = -ww
-        off[(b, a)] = -ww
-        deg[a] += ww
-        deg[b] += ww
-    if off:
-        keys = np.array(list(off.keys()), dtype=np.int64)
-        vals = np.array(list(off.values()))
-        rows = np.concatenate([keys[:, 0], np.arange(nv)])
-        cols = np.concatenate([keys[:, 1], np.arange(nv)])
-        data = np.concatenate([vals, deg])
-    else:
-        rows = cols = np.arange(nv)
-        data = deg
-    # a self loop (a == a) would have been assigned then incremented in the reference; G-set has none
-    L = sp.coo_matrix((data, (rows, cols)), shape=(nv, nv)).tocsr()
-    L.sum_duplicates()
-    L.eliminate_zeros()  # sparse(L) drops explicit zeros
-    return L
-
-
-def maxcut_C(nv, ei, ej, w) -> sp.csr_matrix:
-    """C = -L/4 (example/example_maxcut.m:10-11)."""
-    return (-0.25 * laplacian(nv, ei, ej, w)).tocsr()
-
-
-def maxcut_sedumi(C: sp.spmatrix):
-    """The (At, b, c, K) description of diag(X)=1 used in example/example_maxcut.m:12-21."""
-    n = C.shape[0]
-    rows = np.arange(n) * n + np.arange(n)
-    At = sp.csc_matrix((np.ones(n), (rows, np.arange(n))), shape=(n * n, n))
-    c = np.asarray(C.todense()).reshape(-1, order="F")
-    return At, np.ones(n), c, {"s": n}
-
-
-# --------------------------------------------------------------------------------------------
-# BQP second-order moment relaxation
-# --------------------------------------------------------------------------------------------
-def bqpmom(n: int, Q: np.ndarray, e: np.ndarray):
-    """Restates src/basicfunction/bqpmom.m:6-126.  Returns (At, b, c, K) with At CSC (mb^2 x m),
-    b dense (m,), c dense (mb^2,), K = {'s': mb}."""
-    basis = get_basis(n, 2)
-    basis = basis[:, (basis > 1).sum(axis=0) == 0]  # bqpmom.m:8-14  multilinear monomials
-    mb = basis.shape[1]
-    spb = get_basis(n, 4)
-    keep = ((spb > 2).sum(axis=0) == 0) & ((spb % 2).sum(axis=0) != 0)  # bqpmom.m:16-22
-    spb = spb[:, keep]
-    lsp = spb.shape[1]
-    where = _index_map(spb)
-    mm = [[] for _ in range(lsp)]  # mm[ind] = list of (i, j), i < j, 0-based   bqpmom.m:24-31
-    bt = basis.T
-    for i in range(mb):
-        s = bt[i] + bt[i + 1 :]
-        for off, col in enumerate(s.tolist()):
-            mm[where[tuple(col)]].append((i, i + 1 + off))
-    ncons = mb * (mb + 1) // 2 - lsp + n * (mb - 1) - mb + 1  # bqpmom.m:32
-    row, col, val = [0], [0], [1.0]  # X(1,1) = 1, bqpmom.m:33-37
-    b = np.zeros(ncons)
-    b[0] = 1.0
-    for i in range(1, n + 1):  # bqpmom.m:38-42
-        row += [0, i * mb + i]
-        col += [i, i]
-        val += [0.5, -0.5]
-    l = n + 1
-    for i in range(n + 1, mb):  # bqpmom.m:45-51
-        cc = np.nonzero(basis[:, i] == 1)[0] + 1
-        row += [cc[0] * mb + cc[0], i * mb + i, cc[1] * mb + cc[1], i * mb + i]
-        col += [l, l, l + 1, l + 1]
-        val += [0.5, -0.5, 0.5, -0.5]
-        l += 2
-    loa = []  # bqpmom.m:52-58 : both symmetric positions of every pair
-    for i in range(lsp):
-        a = []
-        for (p, q) in mm[i]:
-            a += [q * mb + p, p * mb + q]
-        loa.append(a)
-    for k in range(n):  # bqpmom.m:59-78   x_k^2 * m_i = m_i
-        for i in range(1, mb):
-            if basis[k, i] == 0:
-                bi = basis[:, i].copy()
-                bi[k] = 2
-                l1 = loa[where[tuple(bi.tolist())]]
-                l2 = loa[where[tuple(basis[:, i].tolist())]]
-                row += l1 + l2
-                col += [l] * (len(l1) + len(l2))
-                if len(l1) < len(l2):
-                    val += [1.0] * len(l1) + [-len(l1) / len(l2)] * len(l2)
-                else:
-                    val += [len(l2) / len(l1)] * len(l1) + [-1.0] * len(l2)
-                l += 1
-    for i in range(lsp):  # bqpmom.m:80-90  entries of one monomial are all equal
-        firsts = [p for (p, _) in mm[i]]
-        idx = int(np.argmax(firsts))
-        for j in range(len(mm[i])):
-            if j != idx:
-                row += loa[i][2 * idx : 2 * idx + 2] + loa[i][2 * j : 2 * j + 2]
-                col += [l] * 4
-                val += [0.5, 0.5, -0.5, -0.5]
-                l += 1
-    assert l == ncons, (l, ncons)
-    At = sp.coo_matrix((val, (row, col)), shape=(mb * mb, ncons)).tocsc()
-    At.sum_duplicates()
-    # objective, bqpmom.m:93-122
-    crow = list(range(1, n + 1))
-    ccol = list(range(1, n + 1))
-    cval = list(np.diag(Q))
-    for i in range(n):
-        cnt = len(mm[i])
-        for (p, q) in mm[i]:
-            crow += [p, q]
-            ccol += [q, p]
-        cval += [e[i] / (2 * cnt)] * (2 * cnt)
-    ind = n
-    for i in range(1, n):
-        for j in range(i):
-            cnt = len(mm[ind])
-            for (p, q) in mm[ind]:
-                crow += [p, q]
-                ccol += [q, p]
-            cval += [Q[j, i] / cnt] * (2 * cnt)
-            ind += 1
-    C = sp.coo_matrix((cval, (crow, ccol)), shape=(mb, mb)).toarray()
-    c = C.reshape(-1, order="F")
-    return At, b, c, {"s": mb}
-
-
-def bqp_bruteforce(Q: np.ndarray, e: np.ndarray) -> float:
-    """min x'Qx + e'x over x in {-1,+1}^n (independent check for small n)."""
-    n = len(e)
-    X = np.array(list(itertools.product([-1.0, 1.0], repeat=n)))
-    vals = np.einsum("bi,ij,bj->b", X, Q, X) + X @ e
-    return float(vals.min())
-
-
-# --------------------------------------------------------------------------------------------
-# quartic on the sphere, second-order moment relaxation
-# --------------------------------------------------------------------------------------------
-def qsmom(n: int, coe: np.ndarray):
-    """Restates src/basicfunction/qsmom.m:6-124."""
-    basis = get_basis(n, 2)
-    mb = basis.shape[1]
-    spb = get_basis(n, 4)
-    lsp = spb.shape[1]
-    assert len(coe) == lsp
-    where = _index_map(spb)
-    mm = [[] for _ in range(lsp)]  # qsmom.m:11-18, i <= j
-    bt = basis.T
-    for i in range(mb):
-        s = bt[i] + bt[i:]
-        for off, colv in enumerate(s.tolist()):
-            mm[where[tuple(colv)]].append((i, i + off))
-    ncons = mb * (mb + 1) // 2 - lsp + mb + 1  # qsmom.m:19
-    row, col, val = [0], [0], [1.0]
-    b = np.zeros(ncons)
-    b[0] = 1.0
-    l = 1
-
-    def entries(ind):
-        """positions contributed by mm[ind]: diagonal pairs once, off-diagonal pairs twice
-        (qsmom.m:39-47).  Order: loa(2j-1:2j) = [(q,p)->q*mb+p ... ] as in qsmom.m:28-31."""
-        out = []
-        for (p, q) in mm[ind]:
-            if p == q:
-                out.append(p * mb + q)
-            else:
-                out += [q * mb + p, p * mb + q]
-        return out
-
-    ent_cache = [entries(i) for i in range(lsp)]
-    eye = np.eye(n, dtype=np.int64)
-    for i in range(mb):  # qsmom.m:33-64   (sum_k x_k^2) * m_i = m_i
-        for k in range(n):
-            ind1 = where[tuple((basis[:, i] + 2 * eye[k]).tolist())]
-            e1 = ent_cache[ind1]
-            row += e1
-            col += [l] * len(e1)
-            val += [1.0 / len(e1)] * len(e1)
-        e2 = ent_cache[where[tuple(basis[:, i].tolist())]]
-        row += e2
-        col += [l] * len(e2)
-        val += [-1.0 / len(e2)] * len(e2)
-        l += 1
-    for i in range(lsp):  # qsmom.m:66-92
-        firsts = [p for (p, _) in mm[i]]
-        idx = int(np.argmax(firsts))
-        pi, qi = mm[i][idx]
-        for j in range(len(mm[i])):
-            if j == idx:
-                continue
-            if pi == qi:
-                row.append(pi * mb + qi); col.append(l); val.append(1.0)
-            else:
-                row += [qi * mb + pi, pi * mb + qi]; col += [l, l]; val += [0.5, 0.5]
-            pj, qj = mm[i][j]
-            if pj == qj:
-                row.append(pj * mb + qj); col.append(l); val.append(-1.0)
-            else:
-                row += [qj * mb + pj, pj * mb + qj]; col += [l, l]; val += [-0.5, -0.5]
-            l += 1
-    assert l == ncons, (l, ncons)
-    At = sp.coo_matrix((val, (row, col)), shape=(mb * mb, ncons)).tocsc()
-    At.sum_duplicates()
-    crow, ccol, cval = [], [], []  # qsmom.m:95-112
-    for i in range(lsp):
-        s = 0
-        for (p, q) in mm[i]:
-            if p == q:
-                crow.append(p); ccol.append(q); s += 1
-            else:
-                crow += [p, q]; ccol += [q, p]; s += 2
-        cval += [coe[i] / s] * s
-    C = sp.coo_matrix((cval, (crow, ccol)), shape=(mb, mb)).toarray()
-    return At, b, C.reshape(-1, order="F"), {"s": mb}
-
-
-# --------------------------------------------------------------------------------------------
-# Lovasz theta
-# --------------------------------------------------------------------------------------------
-def generate_hamming(k: int, d):
-    """Restates example/generate_hamming.m:25-60.  Returns (At, b, c, K); constraint 0 is the trace
-    row (generate_hamming.m:55), the others one per edge in (vertex, bit pattern) order."""
-    n = 1 << k
-    d = [d] if np.isscalar(d) else list(d)
-    bitpat = []
-    for dist in d:  # generate_hamming.m:31-37 : nchoosek(1:k,i) is lexicographic
-        for combo in itertools.combinations(range(k), dist):
-            bitpat.append(sum(1 << bpos for bpos in combo))
-    bitpat = np.array(bitpat, dtype=np.int64)
-    ai, aj = [], []
-    adj_r, adj_c = [], []
-    start = 1  # row 0 = trace
-    for i in range(n):
-        nb = np.bitwise_xor(i, bitpat)
-        nb = nb[nb > i]
-        if len(nb):
-            adj_r += [i] * len(nb) + nb.tolist()
-            adj_c += nb.tolist() + [i] * len(nb)
-            rows = np.arange(start, start + len(nb))
-            ai += rows.tolist() + rows.tolist()
-            aj += (nb * n + i).tolist() + (nb + i * n).tolist()
-            start += len(nb)
-    m = start
-    ai = np.array(ai + [0] * n, dtype=np.int64)
-    aj = np.array(aj + (np.arange(n) * n + np.arange(n)).tolist(), dtype=np.int64)
-    At = sp.coo_matrix((np.ones(len(ai)), (aj, ai)), shape=(n * n, m)).tocsc()
-    Adj = sp.coo_matrix((np.ones(len(adj_r)), (adj_r, adj_c)), shape=(n, n)).toarray()
-    Adj = (Adj > 0).astype(np.float64)
-    c = -(1.0 - Adj).reshape(-1, order="F")  # generate_hamming.m:56
-    b = np.zeros(m)
-    b[0] = 1.0
-    return At, b, c, {"s": n}
-
-
-def theta_random(n: int, nedges_draw: int, seed: int):
-    """example/example_theta.m:2-44 with NumPy's generator in place of MATLAB's rng(1)/randi
-    (MATLAB streams are not reproducible here): C = -J, one constraint X_ij = 0 per sampled edge
-    (i < j, unique) and the trace row LAST (example_theta.m:36-43)."""
-    rng = np.random.default_rng(seed)
-    om = rng.integers(0, n, size=(nedges_draw, 2))
-    om = om[om[:, 0] < om[:, 1]]
-    om = np.unique(om, axis=0)
-    m = len(om)
-    rows = np.concatenate([om[:, 0] * n + om[:, 1], om[:, 1] * n + om[:, 0], np.arange(n) * n + np.arange(n)])
-    cols = np.concatenate([np.arange(m), np.arange(m), np.full(n, m)])
-    At = sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(n * n, m + 1)).tocsc()
-    b = np.zeros(m + 1)
-    b[m] = 1.0
-    c = -np.ones(n * n)
-    return At, b, c, {"s": n}
+"""Instance generators moved to the neutral `instances` package (inputs are shared by the oracle, the tests and
+bench.py); this module keeps the oracle's historical import path."""
+from instances.generators import *  # noqa: F401,F403
+from instances.generators import _index_map  # noqa: F401

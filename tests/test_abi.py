@@ -33,7 +33,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.TrOptions) == 16 + 7 * 8
     assert ctypes.sizeof(_lib.TrInfo) == 4 * 8 + 8 + 16
     assert ctypes.sizeof(_lib.TrIter) == 5 * 8 + 16
-    assert ctypes.sizeof(_lib.KktInfo) == 8 * 8 + 8 + 8
+    assert ctypes.sizeof(_lib.KktInfo) == 8 * 8 + 8 + 8 + 8
 
 
 def test_version_and_error_paths(engine_lib):
