@@ -120,6 +120,44 @@ def test_index_split_is_exact_on_large_linear_indices():
         assert abs(h.cost() - f0) <= 1e-12 * abs(f0)
 
 
+@pytest.mark.parametrize("prob,mode", [("bqp10", "dense"), ("bqp10", "sparse"), ("theta", "auto"), ("qs10", "auto")])
+def test_index_split_read_back_is_bit_exact(prob, mode):
+    """BASELINE north_star: "A(YY') index handling must be bit-exact".  The (i, j) pairs the device kernels index with
+    are read back through the C ABI and compared as INTEGER arrays with r mod n / r div n of At's CSC row indices
+    (ManiSDP_unitdiag.m:153-155 applies A to vec(X) column-major: r = j*n + i)."""
+    from manisdp_matlab_b200 import Handle
+    At, b, c, n = (_bqp(10) if prob == "bqp10" else PROBLEMS[prob]())
+    Ac = At.tocsc()
+    Ac.sort_indices()
+    r = Ac.indices.astype(np.int64)
+    with Handle("unitdiag" if prob == "bqp10" else "general", n, At=Ac, b=b, c=c, force_mode=FORCE[mode]) as h:
+        i, j = h.index_split()
+    assert i.dtype == np.int64 and i.shape == r.shape
+    assert np.array_equal(i, r % n) and np.array_equal(j, r // n)
+
+
+def test_index_split_read_back_large_n():
+    """same read-back where r exceeds 2^32: n = 100 000 (sparse representation), r up to n*n - 1 = 1e10 - 1"""
+    import scipy.sparse as sp
+    from manisdp_matlab_b200 import Handle
+    n = 100000
+    rng = np.random.default_rng(5)
+    ii = rng.integers(0, n, 500)
+    jj = rng.integers(0, n, 500)
+    ii[0], jj[0] = n - 1, n - 1
+    rows = np.concatenate([jj * n + ii, ii * n + jj]).astype(np.int64)
+    cols = np.concatenate([np.arange(500), np.arange(500)])
+    At = sp.csc_matrix((np.ones(1000), (rows, cols)), shape=(n * n, 500))
+    At.sum_duplicates()
+    At.sort_indices()
+    c = sp.csc_matrix((np.array([1.0]), (np.array([0]), np.array([0]))), shape=(n * n, 1))
+    with Handle("general", n, At=At, b=np.zeros(500), c=c) as h:
+        i, j = h.index_split()
+    r = At.indices.astype(np.int64)
+    assert r.max() == n * n - 1 > 2 ** 32
+    assert np.array_equal(i, r % n) and np.array_equal(j, r // n)
+
+
 @pytest.mark.parametrize("kind,prob", [("unitdiag", "bqp10"), ("general", "qs10"), ("unittrace", "theta")])
 @pytest.mark.parametrize("use_graph", [0, 1])
 def test_affine_tr_iterates_match_oracle(kind, prob, use_graph):

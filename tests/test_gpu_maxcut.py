@@ -120,6 +120,41 @@ def test_block_major_product_matches_row_kernel(G1, p, monkeypatch):
     assert logs[0][0] == logs[1][0] and _rel(logs[0][2], logs[1][2]) < 1e-9  # graph mode == stream mode
 
 
+@pytest.mark.parametrize("p", [34, 40, 50, 64])
+def test_lowdeg_batched_kernel_is_bit_identical_to_row_kernel(p, monkeypatch):
+    """k_spmm_lowdeg (32 rows per warp, staged (col, val) pairs; default on the toroidal profile for 32 < ld <= 64) does
+    the row kernel's arithmetic in the row kernel's entry order: gradient and Hessian-product rows are BIT-identical with
+    MANISDP_SPMM_LOWDEG=0 (scalars to reduction order), and everything matches the oracle (G11: 800-vertex torus, degree 4,
+    n not a multiple of 32*8 so the ragged last batch is exercised)."""
+    from manisdp_matlab_b200 import Handle
+    from oracle.manisdp_ref import OnlyUnitDiagProblem
+    G11 = _gset("G11")
+    n = G11.shape[0]
+    Y, rng = _rand_point(n, p, 300 + p)
+    U = rng.standard_normal((n, p))
+    prob = OnlyUnitDiagProblem(G11, p, stale_eG=False)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MANISDP_SPMM_LOWDEG", flag)
+        with Handle("onlyunitdiag", n, C_csc=G11) as h:
+            h.set_Y(Y)
+            f = h.cost()
+            g, gn = h.grad()
+            hv = h.hess(U).copy()
+            info = h.tr_solve(maxiter=5, maxinner=20, tolgradnorm=1e-9)
+            k = h.kkt(delta=4, eig_tol=1e-9)
+            out[flag] = (f, g.copy(), gn, hv, info.cost, h.get_Y().copy(), k.lam_min)
+    f, g, gn, hv, cost, Yend, lam = out["1"]
+    # per-row results are bit-identical; the grid-wide scalar sums run over a different row -> warp assignment
+    assert np.array_equal(g, out["0"][1]) and np.array_equal(hv, out["0"][3])
+    assert abs(f - out["0"][0]) <= 1e-14 * abs(f) and abs(gn - out["0"][2]) <= 1e-14 * gn
+    assert abs(cost - out["0"][4]) <= 1e-9 * abs(cost) and _rel(Yend, out["0"][5]) < 1e-7
+    assert abs(lam - out["0"][6]) <= 1e-9 * (1 + abs(lam))
+    assert abs(f - prob.cost(Y)) <= 1e-12 * abs(f)
+    assert _rel(g, prob.grad(Y)) < 1e-12
+    assert _rel(hv, prob.hess(Y, U)) < 1e-12
+
+
 def test_nonsymmetric_and_empty_rows():
     """column lists of C are used as row lists: (Y*C)(:,j) = sum_i C(i,j) Y(:,i) also for a non-symmetric C with
     empty columns and an isolated vertex (ragged input)."""
@@ -241,6 +276,33 @@ def test_eig_step_matches_dense_eig(G1):
     assert abs(k.dinf - dinf) <= 1e-3 * dinf + 1e-9
     assert k.nneg == min(int((dS < 0).sum()), 8)
     # returned vectors are eigenvectors: residual small relative to the spectrum width
+    R = S @ vecs - vecs * vals
+    assert np.linalg.norm(R, axis=0).max() < 1e-6 * (1 + abs(dS[-1]))
+
+
+@pytest.mark.parametrize("delta", [13, 16, 24])
+def test_eig_step_wide_block(G1, delta):
+    """options.delta > 12 makes the LOBPCG basis wider than the 48-column register Gram (round-1 advisor finding): the
+    tiled Gram path must deliver the same `delta` smallest eigenpairs as a dense eigh; delta > 60 is rejected loudly."""
+    from manisdp_matlab_b200 import Handle
+    from manisdp_matlab_b200._lib import EngineError
+    n = G1.shape[0]
+    Y0, _ = _rand_point(n, 10, 78)
+    with Handle("onlyunitdiag", n, C_csc=G1) as h:
+        h.set_Y(Y0)
+        h.tr_solve(maxiter=3, maxinner=20, tolgradnorm=1e-8)
+        k = h.kkt(delta, 1e-10, 0)
+        vals, vecs = h.get_eigs(delta)
+        Y = h.get_Y()
+        with pytest.raises(EngineError):
+            h.kkt(61, 1e-10, 0)
+    X = Y @ Y.T
+    z = np.asarray(G1.multiply(X).sum(axis=0)).ravel()
+    S = G1.toarray() - np.diag(z)
+    dS, _ = np.linalg.eigh(S)
+    assert k.eig_converged == 1
+    assert np.allclose(vals, dS[:delta], atol=1e-7 * (1 + abs(dS[-1])))
+    assert k.nneg == min(int((dS < 0).sum()), delta)
     R = S @ vecs - vecs * vals
     assert np.linalg.norm(R, axis=0).max() < 1e-6 * (1 + abs(dS[-1]))
 
