@@ -304,7 +304,9 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
     }
     h->C_sorted = sorted ? 1 : 0;
     {  // eligibility of the batched low-degree kernel (spmm.cu: k_spmm_lowdeg, LB_CAP = 320 staged entries per batch)
-      int64_t worst = 0;
+      int64_t worst = 0, maxdeg = 0;
+      for (int64_t j = 0; j < ncols; ++j) maxdeg = std::max<int64_t>(maxdeg, (int64_t)rp[(size_t)j + 1] - rp[(size_t)j]);
+      h->C_maxdeg = (int)std::min<int64_t>(maxdeg, 1 << 30);
       for (int64_t j = 0; j < ncols; j += 32) {
         const int64_t j1 = std::min<int64_t>(ncols, j + 32);
         worst = std::max<int64_t>(worst, (int64_t)rp[(size_t)j1] - rp[(size_t)j]);
@@ -312,6 +314,8 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
       h->C_lowdeg = (ncols > 0 && worst <= 320 && (double)nnz <= 8.0 * (double)ncols) ? 1 : 0;
       const char* eld = getenv("MANISDP_SPMM_LOWDEG");
       if (eld) h->spmm_lowdeg = atoi(eld);
+      const char* epf = getenv("MANISDP_LOWDEG_PF");
+      if (epf) h->spmm_lowdeg_pf = std::max(0, std::min(31, atoi(epf)));
     }
     h->C_far_fraction = nnz ? (double)far / (double)nnz : 0.0;
     uint64_t remote = 0;

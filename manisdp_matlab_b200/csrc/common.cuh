@@ -133,7 +133,7 @@ struct manisdp_handle {
   int spmm_use_bulk = 1;               // 1: cp.async.bulk gather kernel for ld >= 32 ; 0: register gathers only
   // block-major entry stream of C (spmm.cu: launch_bm) for the product on large graphs without locality: entries
   // stored column block by column block as (col, val, row), row-aligned chunks per warp, per-block partial rows
-  int bm_mode = 0;                     // MANISDP_SPMM_BM: 0 off, 1 auto (no locality, operand >= 2x L2), 2 always
+  int bm_mode = 1;                     // MANISDP_SPMM_BM: 0 off, 1 auto (no locality, operand >= 2x L2; default), 2 always
   int bm_B = 0;                        // number of column blocks (0: format not built)
   int *bm_col = nullptr, *bm_row = nullptr, *bm_chunk = nullptr;
   double* bm_val = nullptr;
@@ -146,7 +146,9 @@ struct manisdp_handle {
   int64_t spmm_l2_target = 64ll << 20; // bytes of operand rows per column block
   int C_sorted = 0;                    // rows of C are column-sorted
   int C_lowdeg = 0;                    // every 32-row batch of C has <= 320 entries and the mean degree is <= 8
+  int C_maxdeg = 0;                    // largest number of stored entries in a row of C
   int spmm_lowdeg = 1;                 // 1: batched low-degree kernel when C_lowdeg (MANISDP_SPMM_LOWDEG=0: off)
+  int spmm_lowdeg_pf = 0;              // its L2 prefetch distance in rows (MANISDP_LOWDEG_PF; 0 = off)
   double C_far_fraction = 0.0;         // share of entries whose column is farther than an L2 window from the row
   // split-K workspace of the DMMA GEMM (gemm_f64.cu)
   double* gemm_ws = nullptr;

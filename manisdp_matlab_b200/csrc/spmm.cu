@@ -62,6 +62,7 @@ struct SpmmArgs {
   const double* const* peer_tab;
   int rpr;
   int row0;            // global index of local row 0 (set by launch_pass)
+  int pf;              // k_spmm_lowdeg: rows of L2 prefetch distance (0 = off)
 };
 
 struct SpmmPtrs {
@@ -450,16 +451,24 @@ __global__ void __launch_bounds__(MSDP_THREADS, 4) k_spmm_narrow(const SpmmArgs 
 //     of a row padded with (own row, weight 0) entries so that the loads stay unconditional (the own row is the line
 //     the epilogue reads anyway);
 //   * Y is read and H written with streaming (evict-first) hints: the L2 is kept for the operand rows, which the
-//     neighbouring rows of the grid re-use.
-// Same entry order and arithmetic as k_spmm, so results are bit-identical to it.  Chosen by launch_pass when every
+//     neighbouring rows of the grid re-use;
+//   * the gather width GW is a template parameter chosen from the largest row degree of C (5 on the torus: four
+//     neighbours + the diagonal): no padded gathers, 20 instead of 32 gather registers, four resident blocks per SM;
+//   * optional (a.pf > 0, MANISDP_LOWDEG_PF): `prefetch.global.L2` of the lines row r + pf will read.  MEASURED
+//     COUNTER-PRODUCTIVE on B200 (torus n = 1e6, p = 64: 0.44 ms without, 0.52-0.55 ms with pf = 2..16,
+//     profiles/r2_sweep_torus_pf.txt): the kernel is not DRAM-latency-bound, the extra LSU traffic costs more than it
+//     hides.  Off by default, kept for experiments.
+// Same entry order as k_spmm (which keeps several partial accumulators per row, so rows agree to rounding).  Chosen by launch_pass when every
 // 32-row batch of C has at most LB_CAP entries and the mean degree is <= 8 (api.cu: C_lowdeg).
 #define LB_CAP 320
 #define LB_GW 8
-template <int EPI, bool PEER>
-__global__ void __launch_bounds__(MSDP_THREADS, 3) k_spmm_lowdeg(const SpmmArgs a) {
+__device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int EPI, bool PEER, int GW>
+__global__ void __launch_bounds__(MSDP_THREADS, GW <= 6 ? 4 : 3) k_spmm_lowdeg(const SpmmArgs a) {
+  constexpr int CAP = GW < 8 ? 32 * GW : LB_CAP;  // GW < 8: every row has <= GW entries (api.cu: C_maxdeg)
   __shared__ double sm[2 * 32];
-  __shared__ int s_col[MSDP_THREADS / 32][LB_CAP];
-  __shared__ double s_val[MSDP_THREADS / 32][LB_CAP];
+  __shared__ int s_col[MSDP_THREADS / 32][CAP];
+  __shared__ double s_val[MSDP_THREADS / 32][CAP];
   if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
   const SpmmPtrs p = select_ptrs(a);
   const int* __restrict__ col = a.col;
@@ -480,6 +489,8 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3) k_spmm_lowdeg(const SpmmArgs 
   };
   const int64_t nbatches = (a.nrows + 31) / 32;
   const int64_t nw = (int64_t)gridDim.x * (MSDP_THREADS / 32);
+  const int pf = a.pf;
+  const int nl = (ld * 8 + 127) / 128;  // 128-byte lines per row (<= 4)
   double q[2] = {0.0, 0.0};
   for (int64_t batch = (int64_t)blockIdx.x * (MSDP_THREADS / 32) + wid; batch < nbatches; batch += nw) {
     const int64_t r0 = batch * 32;
@@ -502,6 +513,23 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3) k_spmm_lowdeg(const SpmmArgs 
       const int64_t row = r0 + r;
       const size_t off = (size_t)row * ld + lo;
       const int ownc = a.row0 + (int)row;
+      if (pf > 0) {
+        const int rp = r + pf;
+        // past the end of this batch: the first rows of this warp's NEXT batch (Y / U rows only: its indices are not staged yet)
+        const int64_t prow = rp < nr ? r0 + rp : (batch + nw) * 32 + (rp - nr);
+        const int pe0 = __shfl_sync(0xffffffffu, e0, rp & 31) - E0, pe1 = __shfl_sync(0xffffffffu, e1, rp & 31) - E0;
+        if (prow < a.nrows) {
+          const int seg = lane / nl, ln = lane - seg * nl;  // segment 0: Y row, 1: U row, 2..: gathered rows
+          const size_t lo_pf = (size_t)ln * 16;
+          if (seg == 0) {
+            if (EPI == EPI_HESS) prefetch_l2(p.Y + (size_t)prow * ld + lo_pf);
+          } else if (seg == 1) {
+            prefetch_l2(p.Uown + (size_t)prow * ld + lo_pf);
+          } else if (rp < nr && pe0 + seg - 2 < pe1) {
+            prefetch_l2(operand_row(sc[pe0 + seg - 2]) + lo_pf);
+          }
+        }
+      }
       double2 y = make_double2(0.0, 0.0), u = make_double2(0.0, 0.0);
       double eg = 0.0;
       if (EPI == EPI_HESS) {
@@ -515,18 +543,18 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3) k_spmm_lowdeg(const SpmmArgs 
         eg = p.eG ? p.eG[row] : 0.0;
       }
       double2 acc = make_double2(0.0, 0.0);
-      for (int base = re0; base < re1; base += LB_GW) {
-        double2 g[LB_GW];
-        double w[LB_GW];
+      for (int base = re0; base < re1; base += GW) {
+        double2 g[GW];
+        double w[GW];
 #pragma unroll
-        for (int s = 0; s < LB_GW; ++s) {
+        for (int s = 0; s < GW; ++s) {
           const bool ok = base + s < re1;
           const int c = ok ? sc[base + s] : ownc;
           w[s] = ok ? sv[base + s] : 0.0;
           g[s] = ldg2(operand_row(c) + lo);
         }
 #pragma unroll
-        for (int s = 0; s < LB_GW; ++s) {
+        for (int s = 0; s < GW; ++s) {
           acc.x = fma(w[s], g[s].x, acc.x);
           acc.y = fma(w[s], g[s].y, acc.y);
         }
@@ -811,6 +839,8 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3)
   // The gathers are UNCONDITIONAL: a lane past ld/2 (only when ld < 64) reads vector 0 of the same operand row and
   // never stores.  A predicated `act ? ldg2(..) : 0` made ptxas route every load through a temporary and issue the
   // eight gathers of a group in ~3 dependent batches (round-1 SASS, profiles/r1_blockmajor_product_ab.txt).
+  // The entry stream is read and the partial rows are written with streaming (evict-first) hints: both are touched once
+  // per pass, and write-allocating 8np bytes of partial rows per pass would push the operand block out of the L2.
   const int lo = act ? 2 * lane : 0;
   const int nw = gridDim.x * (MSDP_THREADS / 32);
   for (int ch = blockIdx.x * (MSDP_THREADS / 32) + (threadIdx.x >> 5); ch < nchunks; ch += nw) {
@@ -820,17 +850,17 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3)
     int c = 0, r = -1;
     double w = 0.0;
     if (e0 + lane < e1) {
-      c = __ldg(ecol + e0 + lane);
-      w = __ldg(eval_ + e0 + lane);
-      r = __ldg(erow + e0 + lane);
+      c = __ldcs(ecol + e0 + lane);
+      w = __ldcs(eval_ + e0 + lane);
+      r = __ldcs(erow + e0 + lane);
     }
     for (int base = e0; base < e1; base += 32) {
       int cn = 0, rn = -1;
       double wn = 0.0;
       if (base + 32 + lane < e1) {  // next group's entries before this group's gathers
-        cn = __ldg(ecol + base + 32 + lane);
-        wn = __ldg(eval_ + base + 32 + lane);
-        rn = __ldg(erow + base + 32 + lane);
+        cn = __ldcs(ecol + base + 32 + lane);
+        wn = __ldcs(eval_ + base + 32 + lane);
+        rn = __ldcs(erow + base + 32 + lane);
       }
       const int cnt = min(32, e1 - base);
       int rprev = __shfl_up_sync(0xffffffffu, r, 1);
@@ -849,7 +879,7 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3)
 #pragma unroll
         for (int s = 0; s < BM_U; ++s) {
           if ((chg >> (k + s)) & 1u) {  // warp-uniform
-            if (cur >= 0 && act) st2(part + (size_t)cur * ld + 2 * lane, acc);
+            if (cur >= 0 && act) stcs2(part + (size_t)cur * ld + 2 * lane, acc);
             cur = __shfl_sync(0xffffffffu, r, k + s);
             acc = make_double2(0.0, 0.0);
           }
@@ -862,7 +892,7 @@ __global__ void __launch_bounds__(MSDP_THREADS, 3)
       w = wn;
       r = rn;
     }
-    if (cur >= 0 && act) st2(part + (size_t)cur * ld + 2 * lane, acc);
+    if (cur >= 0 && act) stcs2(part + (size_t)cur * ld + 2 * lane, acc);
   }
 }
 
@@ -955,12 +985,25 @@ static int launch_pass(manisdp_handle* h, SpmmArgs a) {
   if (h->spmm_lowdeg && h->C_lowdeg && a.first && a.last && a.bptr0 == h->C.rowptr && a.ld > 32 && a.ld <= 64 &&
       h->spmm_use_bulk != 2) {
     a.row0 = (int)h->row_begin;
+    a.pf = h->spmm_lowdeg_pf;
     const int nb = (int)std::max<int64_t>(
-        1, std::min<int64_t>((int64_t)h->num_sms * 3, (a.nrows + 32 * (MSDP_THREADS / 32) - 1) / (32 * (MSDP_THREADS / 32))));
-    if (a.peer_tab)
-      k_spmm_lowdeg<EPI, true><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
-    else
-      k_spmm_lowdeg<EPI, false><<<nb, MSDP_THREADS, 0, h->stream>>>(a);
+        1, std::min<int64_t>((int64_t)h->num_sms * 4, (a.nrows + 32 * (MSDP_THREADS / 32) - 1) / (32 * (MSDP_THREADS / 32))));
+    const int gw = h->C_maxdeg <= 4 ? 4 : h->C_maxdeg <= 5 ? 5 : h->C_maxdeg <= 6 ? 6 : 8;
+#define LOWDEG_LAUNCH(GW_)                                                      \
+  do {                                                                          \
+    const int nbw = std::min(nb, h->num_sms * ((GW_) <= 6 ? 4 : 3));            \
+    if (a.peer_tab)                                                             \
+      k_spmm_lowdeg<EPI, true, GW_><<<nbw, MSDP_THREADS, 0, h->stream>>>(a);    \
+    else                                                                        \
+      k_spmm_lowdeg<EPI, false, GW_><<<nbw, MSDP_THREADS, 0, h->stream>>>(a);   \
+  } while (0)
+    switch (gw) {
+      case 4: LOWDEG_LAUNCH(4); break;
+      case 5: LOWDEG_LAUNCH(5); break;
+      case 6: LOWDEG_LAUNCH(6); break;
+      default: LOWDEG_LAUNCH(8); break;
+    }
+#undef LOWDEG_LAUNCH
     KERNEL_CHECK(h);
     return MANISDP_OK;
   }

@@ -74,6 +74,9 @@ def run(name, cpu):
         raise SystemExit(f"unknown config {name}")
     t_gen = time.perf_counter() - t0
     o = dict(opts, verbose="--verbose" in sys.argv)
+    for a in sys.argv[1:]:
+        if a.startswith("--opts="):  # option overrides as JSON, e.g. --opts='{"p0": 256, "delta": 24}'
+            o.update(json.loads(a[len("--opts="):]))
     t0 = time.perf_counter()
     X, obj, data = call(M, o)
     dt = time.perf_counter() - t0
@@ -83,7 +86,8 @@ def run(name, cpu):
                status=data["status"], launches=int(data.get("launches", 0)), gen_seconds=t_gen,
                modes=[data.get("s_mode"), data.get("a_mode")], p_max=max(data["fac_size"]),
                kkt_seconds=data.get("kkt_seconds"), eig_iters=data.get("eig_iters_total"),
-               setup_seconds=data.get("setup_seconds"))
+               setup_seconds=data.get("setup_seconds"), fac_size=data["fac_size"],
+               options={k: v for k, v in o.items() if k != "verbose"})
     if cpu:
         t0 = time.perf_counter()
         Xc, objc, dc = call(ref, dict(opts, seed=0))
