@@ -1,5 +1,6 @@
-/* Minimal stand-in for MATLAB's mex.h: just enough declarations to syntax-check matlab/manisdp_mex.cpp in a container
- * without MATLAB (tests/test_mex_gateway.py).  Not used by any product code. */
+/* Minimal stand-in for MATLAB's mex.h: the declarations matlab/manisdp_mex.cpp needs, in a container without MATLAB.
+ * tests/mex_stub/mex_stub.cpp implements them functionally so that tests/test_mex_gateway.py can EXECUTE the gateway
+ * (create -> set_Y -> tr_solve -> kkt -> get_Y on the GPU).  Not used by any product code. */
 #ifndef MEX_STUB_H
 #define MEX_STUB_H
 #include <stddef.h>
@@ -37,6 +38,7 @@ void mxDestroyArray(mxArray*);
 void mexErrMsgIdAndTxt(const char*, const char*, ...);
 void mexLock(void);
 int mexAtExit(void (*)(void));
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]);
 #ifdef __cplusplus
 }
 #endif
