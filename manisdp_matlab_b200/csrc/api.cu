@@ -314,8 +314,6 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
       h->C_lowdeg = (ncols > 0 && worst <= 320 && (double)nnz <= 8.0 * (double)ncols) ? 1 : 0;
       const char* eld = getenv("MANISDP_SPMM_LOWDEG");
       if (eld) h->spmm_lowdeg = atoi(eld);
-      const char* epf = getenv("MANISDP_LOWDEG_PF");
-      if (epf) h->spmm_lowdeg_pf = std::max(0, std::min(31, atoi(epf)));
     }
     h->C_far_fraction = nnz ? (double)far / (double)nnz : 0.0;
     uint64_t remote = 0;

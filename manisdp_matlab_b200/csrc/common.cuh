@@ -148,7 +148,6 @@ struct manisdp_handle {
   int C_lowdeg = 0;                    // every 32-row batch of C has <= 320 entries and the mean degree is <= 8
   int C_maxdeg = 0;                    // largest number of stored entries in a row of C
   int spmm_lowdeg = 1;                 // 1: batched low-degree kernel when C_lowdeg (MANISDP_SPMM_LOWDEG=0: off)
-  int spmm_lowdeg_pf = 0;              // its L2 prefetch distance in rows (MANISDP_LOWDEG_PF; 0 = off)
   double C_far_fraction = 0.0;         // share of entries whose column is farther than an L2 window from the row
   // split-K workspace of the DMMA GEMM (gemm_f64.cu)
   double* gemm_ws = nullptr;

@@ -62,7 +62,6 @@ struct SpmmArgs {
   const double* const* peer_tab;
   int rpr;
   int row0;            // global index of local row 0 (set by launch_pass)
-  int pf;              // k_spmm_lowdeg: rows of L2 prefetch distance (0 = off)
 };
 
 struct SpmmPtrs {
@@ -454,15 +453,14 @@ __global__ void __launch_bounds__(MSDP_THREADS, 4) k_spmm_narrow(const SpmmArgs 
 //     neighbouring rows of the grid re-use;
 //   * the gather width GW is a template parameter chosen from the largest row degree of C (5 on the torus: four
 //     neighbours + the diagonal): no padded gathers, 20 instead of 32 gather registers, four resident blocks per SM;
-//   * optional (a.pf > 0, MANISDP_LOWDEG_PF): `prefetch.global.L2` of the lines row r + pf will read.  MEASURED
-//     COUNTER-PRODUCTIVE on B200 (torus n = 1e6, p = 64: 0.44 ms without, 0.52-0.55 ms with pf = 2..16,
-//     profiles/r2_sweep_torus_pf.txt): the kernel is not DRAM-latency-bound, the extra LSU traffic costs more than it
-//     hides.  Off by default, kept for experiments.
+//   * (tried and removed: `prefetch.global.L2` of the lines row r + pf will read -- measured counter-productive on
+//     B200, torus n = 1e6, p = 64: 0.44 ms without, 0.52-0.55 ms with pf = 2..16, profiles/r2_sweep_torus_pf.txt; the
+//     ncu capture profiles/r2_ncu_lowdeg_torus_p64.md shows why: the kernel issues 219 warp instructions per row, half
+//     of them address arithmetic, so extra instructions cost more than the latency they hide.)
 // Same entry order as k_spmm (which keeps several partial accumulators per row, so rows agree to rounding).  Chosen by launch_pass when every
 // 32-row batch of C has at most LB_CAP entries and the mean degree is <= 8 (api.cu: C_lowdeg).
 #define LB_CAP 320
 #define LB_GW 8
-__device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int EPI, bool PEER, int GW>
 __global__ void __launch_bounds__(MSDP_THREADS, GW <= 6 ? 4 : 3) k_spmm_lowdeg(const SpmmArgs a) {
   constexpr int CAP = GW < 8 ? 32 * GW : LB_CAP;  // GW < 8: every row has <= GW entries (api.cu: C_maxdeg)
@@ -480,17 +478,18 @@ __global__ void __launch_bounds__(MSDP_THREADS, GW <= 6 ? 4 : 3) k_spmm_lowdeg(c
   const int lo = act ? 2 * lane : 0;  // inactive lanes (ld < 64) shadow vector 0 and never store
   int* sc = s_col[wid];
   double* sv = s_val[wid];
+  // gather address = per-lane base + column * row bytes: one 32 x 32 -> 64-bit multiply-add per gather
+  const char* const Ugl = reinterpret_cast<const char*>(Ug + lo);
+  const unsigned rowbytes = (unsigned)ld * 8u;
   auto operand_row = [&](int c) -> const double* {
     if (PEER) {
       const int owner = c / a.rpr;
-      return a.peer_tab[owner] + (size_t)(c - owner * a.rpr) * ld;
+      return a.peer_tab[owner] + (size_t)(c - owner * a.rpr) * ld + lo;
     }
-    return Ug + (size_t)c * ld;
+    return reinterpret_cast<const double*>(Ugl + (size_t)(unsigned)c * rowbytes);
   };
   const int64_t nbatches = (a.nrows + 31) / 32;
   const int64_t nw = (int64_t)gridDim.x * (MSDP_THREADS / 32);
-  const int pf = a.pf;
-  const int nl = (ld * 8 + 127) / 128;  // 128-byte lines per row (<= 4)
   double q[2] = {0.0, 0.0};
   for (int64_t batch = (int64_t)blockIdx.x * (MSDP_THREADS / 32) + wid; batch < nbatches; batch += nw) {
     const int64_t r0 = batch * 32;
@@ -513,23 +512,6 @@ __global__ void __launch_bounds__(MSDP_THREADS, GW <= 6 ? 4 : 3) k_spmm_lowdeg(c
       const int64_t row = r0 + r;
       const size_t off = (size_t)row * ld + lo;
       const int ownc = a.row0 + (int)row;
-      if (pf > 0) {
-        const int rp = r + pf;
-        // past the end of this batch: the first rows of this warp's NEXT batch (Y / U rows only: its indices are not staged yet)
-        const int64_t prow = rp < nr ? r0 + rp : (batch + nw) * 32 + (rp - nr);
-        const int pe0 = __shfl_sync(0xffffffffu, e0, rp & 31) - E0, pe1 = __shfl_sync(0xffffffffu, e1, rp & 31) - E0;
-        if (prow < a.nrows) {
-          const int seg = lane / nl, ln = lane - seg * nl;  // segment 0: Y row, 1: U row, 2..: gathered rows
-          const size_t lo_pf = (size_t)ln * 16;
-          if (seg == 0) {
-            if (EPI == EPI_HESS) prefetch_l2(p.Y + (size_t)prow * ld + lo_pf);
-          } else if (seg == 1) {
-            prefetch_l2(p.Uown + (size_t)prow * ld + lo_pf);
-          } else if (rp < nr && pe0 + seg - 2 < pe1) {
-            prefetch_l2(operand_row(sc[pe0 + seg - 2]) + lo_pf);
-          }
-        }
-      }
       double2 y = make_double2(0.0, 0.0), u = make_double2(0.0, 0.0);
       double eg = 0.0;
       if (EPI == EPI_HESS) {
@@ -551,7 +533,7 @@ __global__ void __launch_bounds__(MSDP_THREADS, GW <= 6 ? 4 : 3) k_spmm_lowdeg(c
           const bool ok = base + s < re1;
           const int c = ok ? sc[base + s] : ownc;
           w[s] = ok ? sv[base + s] : 0.0;
-          g[s] = ldg2(operand_row(c) + lo);
+          g[s] = ldg2(operand_row(c));
         }
 #pragma unroll
         for (int s = 0; s < GW; ++s) {
@@ -985,7 +967,6 @@ static int launch_pass(manisdp_handle* h, SpmmArgs a) {
   if (h->spmm_lowdeg && h->C_lowdeg && a.first && a.last && a.bptr0 == h->C.rowptr && a.ld > 32 && a.ld <= 64 &&
       h->spmm_use_bulk != 2) {
     a.row0 = (int)h->row_begin;
-    a.pf = h->spmm_lowdeg_pf;
     const int nb = (int)std::max<int64_t>(
         1, std::min<int64_t>((int64_t)h->num_sms * 4, (a.nrows + 32 * (MSDP_THREADS / 32) - 1) / (32 * (MSDP_THREADS / 32))));
     const int gw = h->C_maxdeg <= 4 ? 4 : h->C_maxdeg <= 5 ? 5 : h->C_maxdeg <= 6 ? 6 : 8;
