@@ -11,8 +11,14 @@ accept/reject), continuing from the previous step's point.  value = Hessian prod
 time (max over ranks).  Inputs (C: 0.59 GB, Y and the tCG workspace: 0.5 GB each) are far larger than the 126 MB L2, so
 no L2 flush is needed between iterations ("l2": "inputs>L2").
 
-N > 1 (torchrun, one rank per GPU): the same instance ROW-SHARDED -- strong scaling -- with an NCCL
-all-gather of the thin factor per product and an all-reduce of the tCG scalar packet.
+N > 1 (torchrun, one rank per GPU): the same instance sharded over the ranks -- strong scaling.  Two layouts
+(SURVEY 8e), `--layout`:
+  cols (default)  every rank holds all rows of C and p/N COLUMNS of the factor: the product needs no exchange of the
+                  factor; per-row scalars (n doubles) and the tCG scalar packet are all-reduced (csrc/colshard.cu)
+  rows            every rank holds n/N ROWS: the thin factor is exchanged before every product (peer-memory copies
+                  overlapped with column passes, csrc/dist.cu) and the tCG scalar packet all-reduced
+The line of the chosen layout carries the other one as `alt_layout`, and `parity_check`: one Hessian product of the
+sharded handle against SciPy on sampled rows, on every rank.
 
 The JSON line also carries
   e2e          the same metric through the public C-ABI calls with HOST buffers: set_Y (H2D) + tr_solve + get_Y (D2H)
@@ -186,6 +192,34 @@ def run_reference(args, rank):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def _sharded_parity(h, C, n, p, layout, rank, world, row_begin, row_end, Yfull, seed=11, nrows=4096):
+    """N > 1 self-check (round-1 verdict: SCALE proved speed, not results): one Hessian product of the sharded handle at
+    the start point against SciPy on a random sample of rows -- H = C*U - Y.*rowsum(Y.*(C*U)) - U.*rowsum((C*Y).*Y)
+    (ManiSDP_onlyunitdiag.m:118-119,128-129) -- each rank checking the slice it owns.  Returns the largest relative
+    row error of this rank."""
+    from manisdp_matlab_b200 import _lib
+    rng = np.random.default_rng(seed)
+    U = rng.standard_normal((n, p))
+    rows = np.sort(rng.choice(n, size=min(nrows, n), replace=False))
+    Cs = C.tocsr()[rows]
+    CU, CY = Cs @ U, Cs @ Yfull
+    Yr, Ur = Yfull[rows], U[rows]
+    Href = CU - Yr * np.sum(Yr * CU, axis=1, keepdims=True) - Ur * np.sum(CY * Yr, axis=1, keepdims=True)
+    if layout == "cols":
+        pl = h.p
+        sl = slice(rank * pl, min(p, (rank + 1) * pl))
+        Uloc = np.zeros((n, pl))
+        Uloc[:, :sl.stop - sl.start] = U[:, sl]
+        H = h.hess(Uloc)[rows][:, :sl.stop - sl.start]
+        Href = Href[:, sl]
+    else:
+        H = h.hess(U[row_begin:row_end])
+        keep = (rows >= row_begin) & (rows < row_end)
+        H, Href = H[rows[keep] - row_begin], Href[keep]
+    den = np.maximum(np.linalg.norm(Href, axis=1), 1e-300)
+    return float(np.max(np.linalg.norm(H - Href, axis=1) / den)) if len(den) else 0.0
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -197,34 +231,68 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, C, name, t_gen = build_workload(args)
     p = args.p
-    nccl_id = None
-    row_begin, row_end = 0, n
-    if world > 1:
-        obj = [_lib.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        nccl_id = obj[0]
-        rpr = (n + world - 1) // world
-        row_begin, row_end = min(n, rank * rpr), min(n, (rank + 1) * rpr)
-        Cloc = C[:, row_begin:row_end]  # owned columns == owned rows (C symmetric)
-    else:
-        Cloc = C
-    t0 = time.perf_counter()
-    h = Handle("onlyunitdiag", n, C_csc=Cloc, device=local_rank, rank=rank, world=world, row_begin=row_begin,
-               row_end=row_end, nccl_id=nccl_id)
-    t_create = time.perf_counter() - t0
-    Y0 = start_point(n, p)[row_begin:row_end]
-    Y0p = torch.from_numpy(Y0).pin_memory().numpy() if True else Y0
-    out_host = torch.empty((row_end - row_begin, p), dtype=torch.float64).pin_memory().numpy()
-    h.set_Y(Y0p)
-    use_graph = 0 if world > 1 else args.graph
+    Yfull = start_point(n, p)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        return h.tr_solve(maxiter=1, maxinner=args.inner, tolgradnorm=1e-12, use_graph=use_graph)
+    def open_handle(layout):
+        """layout: 'single' | 'rows' (row-sharded, factor exchanged per product) | 'cols' (column-sharded, per-row scalars
+        all-reduced).  Returns (handle, local start point, row_begin, row_end, seconds to create)."""
+        nccl_id = None
+        if world > 1:
+            obj = [_lib.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            nccl_id = obj[0]
+        t0 = time.perf_counter()
+        if layout == "rows":
+            rpr = (n + world - 1) // world
+            r0, r1 = min(n, rank * rpr), min(n, (rank + 1) * rpr)
+            hh = Handle("onlyunitdiag", n, C_csc=C[:, r0:r1], device=local_rank, rank=rank, world=world, row_begin=r0,
+                        row_end=r1, nccl_id=nccl_id)  # owned columns == owned rows (C symmetric)
+            hh.set_Y(Yfull[r0:r1])
+            return hh, Yfull[r0:r1], r0, r1, time.perf_counter() - t0
+        hh = Handle("onlyunitdiag", n, C_csc=C, device=local_rank, rank=rank, world=world, nccl_id=nccl_id,
+                    layout="cols" if layout == "cols" else "rows")
+        hh.set_Y(Yfull)
+        if layout == "cols":
+            hh.col_split()
+        return hh, hh.get_Y(), 0, n, time.perf_counter() - t0
+
+    layout = "single" if world == 1 else args.layout
+    h, Y0, row_begin, row_end, t_create = open_handle(layout)
+    parity = None
+    if world > 1:
+        err = torch.tensor([_sharded_parity(h, C, n, p, layout, rank, world, row_begin, row_end, Yfull)],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        parity = {"parity_check": "ok" if err.item() < 1e-11 else "FAIL", "max_rel_row_error_vs_scipy": err.item(),
+                  "what": "one Hessian product at the start point, 4096 sampled rows per rank, tolerance 1e-11"}
+        h.set_Y(Y0)
+    Y0p = torch.from_numpy(np.ascontiguousarray(Y0)).pin_memory().numpy()
+    out_host = torch.empty(Y0.shape, dtype=torch.float64).pin_memory().numpy()
+    h.set_Y(Y0p)
+    use_graph = 0 if world > 1 else args.graph
+
+    def step(hh=None):
+        return (hh or h).tr_solve(maxiter=1, maxinner=args.inner, tolgradnorm=1e-12, use_graph=use_graph)
+
+    def timed(hh, steps):
+        barrier()
+        hv_, dev_ = 0, 0.0
+        t0_ = time.perf_counter()
+        for _ in range(steps):
+            info = step(hh)
+            hv_ += info.hv_count
+            dev_ += info.seconds  # CUDA events on the engine's stream, around the whole call
+        barrier()
+        wall_ = time.perf_counter() - t0_
+        tt = torch.tensor([dev_, wall_], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return (hv_, *tt.tolist())
 
     # ---- device-resident metric -------------------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -235,27 +303,15 @@ def run_ours(args, rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    hv, dev_s = 0, 0.0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        info = step()
-        hv += info.hv_count
-        dev_s += info.seconds  # CUDA events on the engine's stream, around the whole call
-    barrier()
-    wall_s = time.perf_counter() - t0
+    hv, dev_s, wall_s = timed(h, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = h.stats().launches_total - l0
-    tt = torch.tensor([dev_s, wall_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_s, wall_s = tt.tolist()
     value = hv / dev_s
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------------
-    # The host owns the factor: every step uploads the current Y from pinned host memory, runs one trust-region
-    # iteration and downloads the updated Y, which is the next step's input (so the work per step is the same as in
-    # the device-resident loop above, plus 2 x n*p*8 bytes over PCIe).
+    # The host owns the factor (its local slice when sharded): every step uploads the current Y from pinned host
+    # memory, runs one trust-region iteration and downloads the updated Y, which is the next step's input (so the work
+    # per step is the same as in the device-resident loop above, plus 2 x the slice over PCIe).
     bufs = [Y0p, out_host]
     h.lib.manisdp_get_Y(h._h, _lib._pf(bufs[0]), 0)
 
@@ -283,6 +339,7 @@ def run_ours(args, rank, world):
     # ---- roofline of the dominant kernel (live CUDA-event timing inside the library) -----------------------------
     st = h.stats()
     U = np.random.default_rng(1).standard_normal(Y0.shape)
+    h.set_Y(Y0p)
     h.slot_set(_lib.SLOT_U, U)
     h.hess_bench(3)
     ms = h.hess_bench(args.hv_reps)
@@ -303,7 +360,7 @@ def run_ours(args, rank, world):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                 "traffic": args.traffic, "algorithmic_bytes_per_launch": st.bytes_per_hv,
                 "ms_per_launch": ms, "gflops": st.flops_per_hv / (ms * 1e-3) / 1e9,
-                "includes_allgather": world > 1}
+                "includes_collectives": world > 1}
     if args.traffic:  # how busy HBM actually is: measured DRAM bytes per launch (ncu) over the live launch time
         roofline["traffic_GBps"] = args.traffic / (ms * 1e-3) / 1e9
         roofline["traffic_frac_of_peak"] = roofline["traffic_GBps"] / peak
@@ -317,6 +374,17 @@ def run_ours(args, rank, world):
             vec[nm] = {"ms_per_launch": vms, "achieved_GBps": vbytes / (vms * 1e-3) / 1e9,
                        "frac": vbytes / (vms * 1e-3) / 1e9 / peak}
     h.close()
+    # ---- the other sharded layout, same instance and step (report both) -------------------------------
+    alt = None
+    if world > 1 and not args.no_alt:
+        other = "rows" if layout == "cols" else "cols"
+        h2, Y02, _, _, _ = open_handle(other)
+        for _ in range(args.warmup):
+            step(h2)
+        hv2, dev2, _ = timed(h2, args.steps)
+        h2.close()
+        alt = {"partition": other, "value": hv2 / dev2, "unit": UNIT, "ms_per_step": 1e3 * dev2 / max(1, args.steps),
+               "hv": hv2}
     secondary = None
     if world == 1 and args.workload == "er" and not args.no_secondary:
         secondary = torus_secondary(args, peak)
@@ -339,13 +407,17 @@ def run_ours(args, rank, world):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "n": n, "p": p, "nnzC": int(C.nnz), "step": f"tr_solve(TR_maxiter=1, "
                        f"TR_maxinner={args.inner})", "l2": "inputs>L2", "tcg_loop": "cuda-graph WHILE" if use_graph
-                       else "stream", "partition": "rows" if world > 1 else "single"},
+                       else "stream", "partition": layout},
             "hv": hv, "wall_ms_per_step": 1e3 * wall_s / max(1, args.steps),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(Y0.nbytes),
                     "d2h_bytes_per_step": int(out_host.nbytes) + 256, "steps": ne},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "setup_s": {"generate": t_gen, "create": t_create}, "kkt": kkt, "secondary": secondary,
             "vector_kernels": vec}
+    if parity:
+        line.update(parity)
+    if alt:
+        line["alt_layout"] = alt
     print(json.dumps(line), flush=True)
 
 
@@ -437,6 +509,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kkt", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--layout", choices=["cols", "rows"], default="cols",
+                    help="N > 1: column-sharded (per-row scalars all-reduced; default) or row-sharded (factor exchanged)")
+    ap.add_argument("--no-alt", action="store_true", help="N > 1: skip the measurement of the other layout")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
     args = ap.parse_args()
     if args.cpu_inner is None:

@@ -92,8 +92,13 @@ typedef struct {
   int64_t row_begin, row_end;
   const void *nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (world > 1), else NULL */
   int32_t force_mode;         /* 0 auto; bit0 force dense S; bit1 force sparse S; bit2 force dense A; bit3 force sparse A */
-  int32_t reserved;
+  /* world > 1 only.  MANISDP_SHARD_ROWS (0): the row sharding described above.  MANISDP_SHARD_COLS (1): every rank
+   * holds ALL rows of C (C_jc/C_ir/C_pr describe the whole matrix, row_begin = 0, row_end = n) and, between
+   * manisdp_col_split and manisdp_col_merge, ceil(p/world) COLUMNS of the factor: the Hessian product needs no exchange
+   * of the factor, only all-reduces of per-row scalars (n doubles) -- SURVEY 8e "p-sharding". */
+  int32_t shard_layout;
 } manisdp_problem;
+enum { MANISDP_SHARD_ROWS = 0, MANISDP_SHARD_COLS = 1 };
 
 /* trust-region options: trustregions.m:340-372 defaults are applied for fields left at 0 */
 typedef struct {
@@ -221,6 +226,14 @@ typedef struct {
   double flops_per_hv;
 } manisdp_stats;
 int manisdp_get_stats(manisdp_t *h, manisdp_stats *out);
+/* Column-sharded handles (shard_layout = MANISDP_SHARD_COLS), collective over the ranks.  A handle is created MERGED:
+ * every rank holds the same full-width factor and set_Y / rand_Y / kkt / rank_cut / escape run identically
+ * (deterministically) on every rank.  manisdp_col_split keeps columns [rank*pl, (rank+1)*pl), pl = ceil(p/world), of the
+ * current point for the trust-region solve (the factor width becomes world*pl: zero columns are appended when world
+ * does not divide p); manisdp_col_merge all-gathers the slices back.  While split, only tr_solve, cost, grad, hess,
+ * hess_bench, get_Y / set_Y / slot access (on the local n x pl slice) and get_stats are available. */
+int manisdp_col_split(manisdp_t *h);
+int manisdp_col_merge(manisdp_t *h);
 /* read-back of the integer index split r = j*n + i -> (i, j) of every stored entry of At, in CSC order, exactly as
  * the device kernels index with it (SURVEY 7 "index exactness"; BASELINE north_star: "A(YY') index handling must be
  * bit-exact").  *count = nnz(At); at most `cap` pairs are written; i / j may be NULL to query the count. */

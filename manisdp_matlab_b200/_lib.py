@@ -29,7 +29,7 @@ class Problem(C.Structure):
                 ("At_jc", _u64p), ("At_ir", _u64p), ("At_pr", _f64p),
                 ("b", _f64p), ("c_ir", _u64p), ("c_pr", _f64p), ("c_nnz", C.c_int64),
                 ("rank", C.c_int32), ("world", C.c_int32), ("row_begin", C.c_int64), ("row_end", C.c_int64),
-                ("nccl_unique_id", C.c_void_p), ("force_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("nccl_unique_id", C.c_void_p), ("force_mode", C.c_int32), ("shard_layout", C.c_int32)]
 
 
 class TrOptions(C.Structure):
@@ -98,6 +98,8 @@ SIGNATURES = {
     "manisdp_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "manisdp_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
     "manisdp_test_sym_eig": (C.c_int, [_f64p, C.c_int32, _f64p, _f64p]),
+    "manisdp_col_split": (C.c_int, [_H]),
+    "manisdp_col_merge": (C.c_int, [_H]),
     "manisdp_get_index_split": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,
                                           C.POINTER(C.c_int64)]),
 }
@@ -147,7 +149,7 @@ class Handle:
     """Thin object wrapper over manisdp_t*; every method maps 1:1 onto a C-ABI call."""
 
     def __init__(self, kind, n, *, C_csc=None, At=None, b=None, c=None, device=0, rank=0, world=1,
-                 row_begin=0, row_end=None, nccl_id=None, force_mode=0):
+                 row_begin=0, row_end=None, nccl_id=None, force_mode=0, layout="rows"):
         import scipy.sparse as sp
 
         self.lib = load()
@@ -160,6 +162,8 @@ class Handle:
         pb.row_begin = row_begin
         pb.row_end = n if row_end is None else row_end
         pb.force_mode = force_mode
+        pb.shard_layout = {"rows": 0, "cols": 1}[layout]
+        self.layout, self.rank, self.world = layout, rank, world
         keep = []
         if pb.kind == ONLYUNITDIAG:
             Cm = sp.csc_matrix(C_csc)
@@ -352,6 +356,14 @@ class Handle:
         a = C.c_double()
         self._ck(self.lib.manisdp_line_search(self._h, C.byref(a)), "line_search")
         return a.value
+
+    def col_split(self):
+        """column-sharded handle: keep this rank's ceil(p/world) columns of the factor (collective)"""
+        self._ck(self.lib.manisdp_col_split(self._h), "col_split")
+
+    def col_merge(self):
+        """column-sharded handle: all-gather the column slices back into the full-width factor (collective)"""
+        self._ck(self.lib.manisdp_col_merge(self._h), "col_merge")
 
     def index_split(self):
         """(i, j) int64 arrays of every stored entry of At, CSC order, as the device kernels index with them"""

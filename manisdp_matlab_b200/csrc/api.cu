@@ -352,7 +352,8 @@ static int create_impl(manisdp_handle* h, const manisdp_problem* pb) {
   h->device = pb->device;
   h->n = pb->n;
   h->m = pb->m;
-  h->world = pb->world > 1 ? pb->world : 1;
+  const bool col_layout = (pb->shard_layout == MANISDP_SHARD_COLS);
+  h->world = (pb->world > 1 && !col_layout) ? pb->world : 1;
   h->rank = h->world > 1 ? pb->rank : 0;
   int ndev = 0;
   CUDA_TRY(h, cudaGetDeviceCount(&ndev));
@@ -379,6 +380,13 @@ static int create_impl(manisdp_handle* h, const manisdp_problem* pb) {
     h->row_end = h->n;
   }
   h->nloc = h->row_end - h->row_begin;
+  if (col_layout) {
+    if (h->kind != MANISDP_ONLYUNITDIAG)
+      return msdp_fail(h, MANISDP_E_ARG, "column sharding is implemented for ONLYUNITDIAG (SURVEY 8e: configs 2-4 stay on one GPU)");
+    if (pb->row_begin != 0 || (pb->row_end != 0 && pb->row_end != pb->n))
+      return msdp_fail(h, MANISDP_E_ARG, "column-sharded handle: every rank holds all rows (row_begin = 0, row_end = n)");
+    MSDP_TRY(msdp_col_init(h, pb->nccl_unique_id, pb->world, pb->rank));
+  }
   CUDA_TRY(h, cudaMalloc((void**)&h->st, sizeof(RtrState)));
   CUDA_TRY(h, cudaMemset(h->st, 0, sizeof(RtrState)));
   CUDA_TRY(h, cudaMallocHost((void**)&h->st_host, sizeof(RtrState)));
@@ -409,6 +417,7 @@ static void free_all(manisdp_handle* h) {
   msdp_invalidate_graph(h);
   msdp_eig_release(h);
   msdp_dist_destroy(h);
+  msdp_col_destroy(h);
   msdp_affine_free(h);
   double* arrs[] = {h->Ybuf[0], h->Ybuf[1], h->Gbuf[0], h->Gbuf[1], h->eta[0], h->eta[1], h->r, h->d, h->Hd,
                     h->Uslot, h->Hslot, h->gatherbuf, h->eG[0], h->eG[1], h->zdiag, h->partials, h->C.val,
@@ -480,6 +489,7 @@ int manisdp_get_p(manisdp_t* h, int64_t* p) {
 }
 
 int manisdp_rand_Y(manisdp_t* h, int64_t p, uint64_t seed) {
+  if (h && h->col_split) return msdp_fail(h, MANISDP_E_STATE, "rand_Y: the handle is column-split (manisdp_col_merge first)");
   if (!h) return MANISDP_E_ARG;
   CUDA_TRY(h, cudaSetDevice(h->device));
   MSDP_TRY(msdp_resize(h, p));
@@ -614,6 +624,7 @@ int manisdp_hess_bench(manisdp_t* h, int32_t reps, double* ms_per_hv) {
 }
 
 int manisdp_retract(manisdp_t* h, int32_t eta_slot, int32_t dst_slot) {
+  if (h && h->col_split) return msdp_fail(h, MANISDP_E_STATE, "retract: the handle is column-split (manisdp_col_merge first)");
   if (!h || h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "retract: no factor set");
   double *e = slot_ptr(h, eta_slot), *dst = slot_ptr(h, dst_slot);
   if (!e || !dst || dst == h->Ybuf[h->pt]) return msdp_fail(h, MANISDP_E_ARG, "retract: bad slots");
@@ -624,6 +635,7 @@ int manisdp_retract(manisdp_t* h, int32_t eta_slot, int32_t dst_slot) {
 }
 
 int manisdp_project(manisdp_t* h, int32_t src_slot, int32_t dst_slot) {
+  if (h && h->col_split) return msdp_fail(h, MANISDP_E_STATE, "project: the handle is column-split (manisdp_col_merge first)");
   if (!h || h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "project: no factor set");
   double *s = slot_ptr(h, src_slot), *dst = slot_ptr(h, dst_slot);
   if (!s || !dst || dst == h->Ybuf[h->pt]) return msdp_fail(h, MANISDP_E_ARG, "project: bad slots");
@@ -649,6 +661,7 @@ int manisdp_tr_log(manisdp_t* h, manisdp_tr_iter* buf, int32_t cap, int32_t* cou
 }
 
 int manisdp_kkt(manisdp_t* h, int32_t delta, double eig_tol, int32_t update_dual, manisdp_kkt_info* out) {
+  if (h && h->col_split) return msdp_fail(h, MANISDP_E_STATE, "kkt: the handle is column-split (manisdp_col_merge first)");
   if (!h || !out) return MANISDP_E_ARG;
   if (h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "kkt: no factor set");
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -669,12 +682,14 @@ int manisdp_get_eigs(manisdp_t* h, double* vals, double* vecs, int32_t cap) {
 }
 
 int manisdp_rank_cut(manisdp_t* h, double theta, int32_t apply, int64_t* r, int64_t* p_new) {
+  if (h && h->col_split) return msdp_fail(h, MANISDP_E_STATE, "rank_cut: the handle is column-split (manisdp_col_merge first)");
   if (!h || h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "rank_cut: no factor set");
   CUDA_TRY(h, cudaSetDevice(h->device));
   return msdp_rank_cut(h, theta, apply, r, p_new);
 }
 
 int manisdp_escape(manisdp_t* h, int32_t nne, double alpha, int32_t line_search) {
+  if (h && h->col_split) return msdp_fail(h, MANISDP_E_STATE, "escape: the handle is column-split (manisdp_col_merge first)");
   if (!h || h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "escape: no factor set");
   CUDA_TRY(h, cudaSetDevice(h->device));
   return msdp_escape(h, nne, alpha, line_search);
@@ -715,9 +730,21 @@ int manisdp_get_stats(manisdp_t* h, manisdp_stats* out) {
 }  // extern "C"
 
 extern "C" int manisdp_line_search(manisdp_t* h, double* alpha) {
+  if (h && h->col_split) return msdp_fail(h, MANISDP_E_STATE, "line_search: the handle is column-split (manisdp_col_merge first)");
   if (!h || h->p <= 0) return msdp_fail(h, MANISDP_E_STATE, "line_search: no factor set");
   CUDA_TRY(h, cudaSetDevice(h->device));
   return msdp_line_search(h, alpha);
+}
+
+extern "C" int manisdp_col_split(manisdp_t* h) {
+  if (!h) return MANISDP_E_ARG;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return msdp_col_split(h);
+}
+extern "C" int manisdp_col_merge(manisdp_t* h) {
+  if (!h) return MANISDP_E_ARG;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return msdp_col_merge(h);
 }
 
 extern "C" int manisdp_get_index_split(manisdp_t* h, int64_t* i, int64_t* j, int64_t cap, int64_t* count) {

@@ -169,6 +169,12 @@ struct manisdp_handle {
   const double* const* cg_peer_tab = nullptr;  // set around a cost+grad product that gathers from peers in place
   double C_remote_fraction = 1.0;       // share of the shard's entries whose column is owned by another rank
   double peer_gather_max_remote = 0.05; // direct peer gathers only below this share (MANISDP_PEER_GATHER_MAX)
+  // column-sharded layout (colshard.cu): every rank holds all rows; split = only pl = ceil(p/G) columns of the factor
+  int col_mode = 0, cworld = 1, crank = 0;
+  int col_split = 0;                    // 1 between manisdp_col_split and manisdp_col_merge
+  int col_pfull = 0;                    // width of the factor at the last split
+  void* col_comm = nullptr;             // ncclComm_t
+  double* col_rowvec = nullptr;         // n: per-row partial sums on their way through the all-reduce
   std::string err;
 };
 

@@ -43,3 +43,16 @@ int msdp_spmm_shift(manisdp_handle* h, const double* Vgather, const double* Vown
                     const double* zdiag);
 int msdp_launch_tr_decide_scalar(manisdp_handle* h);
 int msdp_launch_tcg_after_hv_scalar(manisdp_handle* h);
+
+int msdp_spmm_shift_tcg(manisdp_handle* h, const double* V, double* out, int ld, int in_tcg);
+// colshard.cu (column-sharded handle: every rank holds all rows and pl = ceil(p / G) columns)
+int msdp_col_init(manisdp_handle* h, const void* unique_id, int world, int rank);
+void msdp_col_destroy(manisdp_handle* h);
+int msdp_col_split(manisdp_handle* h);
+int msdp_col_merge(manisdp_handle* h);
+int msdp_col_hess(manisdp_handle* h, const double* D, double* Hout, int from_state, int tail_mode);
+int msdp_col_costgrad(manisdp_handle* h, int buf);  // leaves the all-reduced (sum eG, |G|^2) in st->tmp[0..1]
+int msdp_col_retract(manisdp_handle* h);
+int msdp_col_tcg_dir(manisdp_handle* h);
+int msdp_col_allreduce_tmp(manisdp_handle* h, int count);
+int msdp_col_cg_scalar(manisdp_handle* h, int cg_mode);  // scalar tail of a cost+grad call (CG_* modes)

@@ -56,6 +56,12 @@ static int tcg_hv(manisdp_handle* h) {
 
 static int tcg_iteration(manisdp_handle* h, cudaGraphConditionalHandle cond, int use_cond) {
   MSDP_TRY(tcg_hv(h));
+  if (h->col_split) {
+    MSDP_TRY(msdp_launch_tcg_update(h, cond, 0, 1));
+    MSDP_TRY(msdp_col_allreduce_tmp(h, 6));
+    MSDP_TRY(msdp_launch_tcg_after_update_scalar(h));
+    return msdp_col_tcg_dir(h);
+  }
   if (h->world > 1) {
     MSDP_TRY(msdp_launch_tcg_update(h, cond, 0, 1));
     MSDP_TRY(msdp_dist_allreduce_tmp(h, 6));
@@ -67,6 +73,10 @@ static int tcg_iteration(manisdp_handle* h, cudaGraphConditionalHandle cond, int
 }
 
 static int tr_tail(manisdp_handle* h) {
+  if (h->col_split) {
+    MSDP_TRY(msdp_col_retract(h));
+    return msdp_costgrad(h, -1, CG_TR);
+  }
   MSDP_TRY(msdp_launch_retract(h, nullptr, nullptr, nullptr, 1));
   if (h->world > 1) {
     // the proposal lives in Ybuf[pt^1]; pt on the host mirrors the device between iterations
@@ -175,7 +185,7 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
   if (opt.rho_regularization <= 0) opt.rho_regularization = 1e3;
   if (opt.Delta_bar <= 0) opt.Delta_bar = typicaldist;
   if (opt.Delta0 <= 0) opt.Delta0 = opt.Delta_bar / 8.0;
-  const int use_graph = (opt.use_graph != 0) && (h->world <= 1);
+  const int use_graph = (opt.use_graph != 0) && (h->world <= 1) && !h->col_split;
   h->y_version++;
 
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
@@ -238,9 +248,11 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
       // row-sharded handle (an all-gather of the factor each), so those are issued one at a time: a 20 us flag read
       // per iteration against a >= 1 ms exchange.  Single-GPU stream mode grows the chunk instead, and so does the
       // direct peer-gather path (no exchange: a stopped iteration is three tiny all-reduces and no-op kernels).
-      const bool cheap_stop = (h->world <= 1);
-      const int chunk_cap = cheap_stop ? 32 : (msdp_peer_gather_ok(h) ? 4 : 1);
-      int chunk = cheap_stop ? 4 : (msdp_peer_gather_ok(h) ? 2 : 1);
+      // (column-sharded: a stopped iteration still runs its three small all-reduces, ~0.1 ms: short chunks)
+      const bool col_comm = h->col_split && h->cworld > 1;
+      const bool cheap_stop = (h->world <= 1) && !col_comm;
+      const int chunk_cap = cheap_stop ? 32 : ((col_comm || msdp_peer_gather_ok(h)) ? 4 : 1);
+      int chunk = cheap_stop ? 4 : ((col_comm || msdp_peer_gather_ok(h)) ? 2 : 1);
       while (!done && issued < opt.maxinner) {
         int c = chunk;
         if (c > opt.maxinner - issued) c = opt.maxinner - issued;

@@ -206,7 +206,7 @@ __device__ __forceinline__ void spmm_tail(const SpmmArgs& a, double (&q)[2], dou
 template <int GS, int VPL, int EPI, bool PEER>
 __global__ void __launch_bounds__(MSDP_THREADS) k_spmm(const SpmmArgs a) {
   __shared__ double sm[2 * 32];
-  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  if ((EPI == EPI_HESS || EPI == EPI_SHIFT) && a.mode != TAIL_NONE && a.st->stop != 0) return;
   const SpmmPtrs p = select_ptrs(a);
   const int* __restrict__ col = a.col;
   const double* __restrict__ val = a.val;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_spmm(const SpmmArgs a) {
 template <int GS, int EPI, bool PEER>
 __global__ void __launch_bounds__(MSDP_THREADS, 4) k_spmm_narrow(const SpmmArgs a) {
   __shared__ double sm[2 * 32];
-  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  if ((EPI == EPI_HESS || EPI == EPI_SHIFT) && a.mode != TAIL_NONE && a.st->stop != 0) return;
   const SpmmPtrs p = select_ptrs(a);
   const int* __restrict__ col = a.col;
   const double* __restrict__ val = a.val;
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(MSDP_THREADS, GW <= 6 ? 4 : 3) k_spmm_lowdeg(c
   __shared__ double sm[2 * 32];
   __shared__ int s_col[MSDP_THREADS / 32][CAP];
   __shared__ double s_val[MSDP_THREADS / 32][CAP];
-  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  if ((EPI == EPI_HESS || EPI == EPI_SHIFT) && a.mode != TAIL_NONE && a.st->stop != 0) return;
   const SpmmPtrs p = select_ptrs(a);
   const int* __restrict__ col = a.col;
   const double* __restrict__ val = a.val;
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(BULK_WARPS * 32) k_spmm_bulk(const SpmmArgs a)
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ double sm[2 * 32];
   __shared__ uint64_t bars[BULK_WARPS * 2];
-  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  if ((EPI == EPI_HESS || EPI == EPI_SHIFT) && a.mode != TAIL_NONE && a.st->stop != 0) return;
   const SpmmPtrs p = select_ptrs(a);
   const int* __restrict__ col = a.col;
   const double* __restrict__ val = a.val;
@@ -812,7 +812,7 @@ template <int EPI>
 __global__ void __launch_bounds__(MSDP_THREADS, 3)
     k_bm_pass(const SpmmArgs a, const int* __restrict__ ecol, const double* __restrict__ eval_,
               const int* __restrict__ erow, const int* __restrict__ chunk_ptr, int nchunks, double* __restrict__ part) {
-  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  if ((EPI == EPI_HESS || EPI == EPI_SHIFT) && a.mode != TAIL_NONE && a.st->stop != 0) return;
   const SpmmPtrs p = select_ptrs(a);
   const double* __restrict__ Ug = p.Ug;
   const int ld = a.ld;
@@ -886,7 +886,7 @@ template <int EPI, int NB>
 __global__ void __launch_bounds__(MSDP_THREADS)
     k_bm_finish(const SpmmArgs a, const double* __restrict__ part) {
   __shared__ double sm[2 * 32];
-  if (EPI == EPI_HESS && a.mode != TAIL_NONE && a.st->stop != 0) return;
+  if ((EPI == EPI_HESS || EPI == EPI_SHIFT) && a.mode != TAIL_NONE && a.st->stop != 0) return;
   const SpmmPtrs p = select_ptrs(a);
   const int ld = a.ld;
   const int gl = threadIdx.x & 31;
@@ -1187,5 +1187,18 @@ int msdp_spmm_shift(manisdp_handle* h, const double* Vgather, const double* Vown
   a.out = out;
   a.eG = zdiag;
   a.sel = 0;
+  return launch_spmm<EPI_SHIFT>(h, a);
+}
+
+// out = C*V, the raw product of the column-sharded closures (colshard.cu).  in_tcg: a no-op once tCG has stopped.
+int msdp_spmm_shift_tcg(manisdp_handle* h, const double* V, double* out, int ld, int in_tcg) {
+  SpmmArgs a = base_args(h);
+  a.ld = ld;
+  a.Ug = V;
+  a.Uown = V;
+  a.out = out;
+  a.eG = nullptr;
+  a.sel = 0;
+  a.mode = in_tcg ? TAIL_TCG : TAIL_NONE;
   return launch_spmm<EPI_SHIFT>(h, a);
 }
