@@ -388,6 +388,10 @@ def run_ours(args, rank, world):
     secondary = None
     if world == 1 and args.workload == "er" and not args.no_secondary:
         secondary = torus_secondary(args, peak)
+        try:
+            secondary["affine_kernels"] = affine_secondary(args, peak)
+        except Exception as e:  # a secondary measurement must not take the headline line down
+            secondary["affine_kernels"] = {"error": repr(e)}
     if rank != 0:
         return
     # ---- CPU baseline (bounded sample) + config-1 time-to-KKT ----------------------------------------------------
@@ -470,24 +474,114 @@ def time_to_kkt():
     return [out, time_to_kkt_bqp60()]
 
 
+_BQP60 = {}
+
+
+def _bqp60_instance():
+    """SeDuMi data of BASELINE config 2 (built once per process: the Python generator takes ~10 s)."""
+    if not _BQP60:
+        from instances import generators as G
+        d = np.load(os.path.join(ROOT, "tests", "golden", "bqp_60_1.npz"))
+        t0 = time.perf_counter()
+        At, b, c, K = G.bqpmom(60, d["Q"], d["e"])
+        c = c / np.abs(c).max()  # example/example_bqp.m:31-41
+        b = np.asarray(b.todense()).ravel() if hasattr(b, "todense") else np.asarray(b).ravel()
+        _BQP60.update(At=At, b=b, c=c, K=K, t_gen=time.perf_counter() - t0)
+    return _BQP60
+
+
 def time_to_kkt_bqp60():
     """BASELINE config 2: BQP q = 60 (n = 1831, m = 1 155 281) through the drop-in ManiSDP_unitdiag, tol 1e-8."""
-    from instances import generators as G
     from manisdp_matlab_b200 import ManiSDP_unitdiag
-    d = np.load(os.path.join(ROOT, "tests", "golden", "bqp_60_1.npz"))
-    t0 = time.perf_counter()
-    At, b, c, K = G.bqpmom(60, d["Q"], d["e"])
-    c = c / np.abs(c).max()  # example/example_bqp.m:31-41
-    t_gen = time.perf_counter() - t0
+    I = _bqp60_instance()
+    At, b, c, K = I["At"], I["b"], I["c"], I["K"]
     t0 = time.perf_counter()
     X, obj, data = ManiSDP_unitdiag(At, b, c, K, dict(tol=1e-8, verbose=False))
     dt = time.perf_counter() - t0
-    return {"instance": "BQP q=60 (bqp_Q_60_1 / bqp_e_60_1), ManiSDP_unitdiag", "n": int(K["s"]), "m": int(At.shape[1]),
-            "seconds": dt, "obj": obj, "eta": max(data["gap"], data["pinf"], data["dinf"]), "iters": int(data["iters"]),
-            "hv": int(data["hv_count"]), "tr_seconds": data["tr_seconds"],
-            "hv_per_s": data["hv_count"] / max(data["tr_seconds"], 1e-9), "status": data["status"],
-            "generate_seconds": t_gen, "known_optimum": -201.01858191,
-            "cpu_port_seconds_build_container": 353.0}
+    known = None
+    try:
+        known = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_outputs_large.json")))["bqp_60_1_opt"]
+    except Exception:
+        pass
+    out = {"instance": "BQP q=60 (bqp_Q_60_1 / bqp_e_60_1), ManiSDP_unitdiag", "n": int(K["s"]), "m": int(At.shape[1]),
+           "seconds": dt, "obj": obj, "eta": max(data["gap"], data["pinf"], data["dinf"]), "iters": int(data["iters"]),
+           "hv": int(data["hv_count"]), "tr_seconds": data["tr_seconds"],
+           "hv_per_s": data["hv_count"] / max(data["tr_seconds"], 1e-9), "status": data["status"],
+           "generate_seconds": I["t_gen"]}
+    if known:  # optimum pinned by the oracle (tests/golden/make_golden_large.py); asserted in tests/test_gpu_baseline_configs.py
+        out.update(oracle_optimum=known["obj_scaled"], rel_err_vs_oracle=abs(obj - known["obj_scaled"]) / abs(known["obj_scaled"]),
+                   oracle_seconds_build_container=known.get("oracle_seconds"))
+    return out
+
+
+def fp64_gemm_peak():
+    """FP64 GEMM rate of this box as the DENOMINATOR for K4 (no FP64 figure is in MEASURED_PEAKS.json).
+    cuBLAS through torch.matmul is the measurement, not the product: best of 5, 6144^3, CUDA events."""
+    import torch
+    N = 6144
+    a = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    b = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * N ** 3 / (best * 1e-3) / 1e12
+
+
+def affine_secondary(args, peak):
+    """K2 / K3 / K4 measured where they dominate, one Hessian product each (manisdp_hess_bench):
+      * sparse path -- theta of Hamming(11,2) (n = 2048, m = 56 321; BASELINE config 4 at its largest member) through the
+        ManiSDP_unittrace closures: SDDMM gather over the At pattern + scatter-SpMM, HBM / L2-bound;
+      * dense path -- BQP q = 60 (config 2) through the ManiSDP_unitdiag closures at p = 100 and p = 300: three FP64 DMMA
+        GEMMs of n x n x p per product, against the cuBLAS DGEMM rate measured on this box."""
+    from instances import generators as G
+    from manisdp_matlab_b200 import Handle, _lib
+    out = {}
+    dgemm = fp64_gemm_peak()
+    out["fp64_dgemm_peak_tflops"] = {"value": dgemm, "how": "torch.matmul float64 6144^3 (cuBLAS), best of 5, CUDA events"}
+    At, b, c, K = G.generate_hamming(11, 2)
+    n = int(K["s"])
+    b = np.asarray(b.todense()).ravel() if hasattr(b, "todense") else np.asarray(b).ravel()
+    with Handle("unittrace", n, At=At, b=b, c=c) as h:
+        h.set_dual(np.zeros(At.shape[1]), 1e5)
+        rows = []
+        for p in (8, 20, 32):
+            h.rand_Y(p, 1)
+            h.slot_set(_lib.SLOT_U, np.random.default_rng(1).standard_normal((n, p)))
+            h.hess_bench(5)
+            ms = h.hess_bench(50)
+            st = h.stats()
+            ach = st.bytes_per_hv / (ms * 1e-3) / 1e9
+            rows.append({"p": p, "ms_per_hv": ms, "algorithmic_bytes": st.bytes_per_hv, "achieved_GBps": ach,
+                         "frac_of_hbm_peak": ach / peak, "s_mode": int(st.s_mode), "a_mode": int(st.a_mode)})
+    out["theta_hamming_11_2_sparse_path"] = {
+        "n": n, "m": int(At.shape[1]), "nnzA": int(At.nnz), "kernels": "K2 sddmm_AYY + K3 scatter_spmm (affine.cu)",
+        "note": "working set (At pattern 0.9 MB + n x p factor) sits in L2: launch- and latency-bound, not an HBM stream",
+        "rows": rows}
+    I = _bqp60_instance()
+    n = int(I["K"]["s"])
+    with Handle("unitdiag", n, At=I["At"], b=I["b"], c=I["c"]) as h:
+        h.set_dual(np.zeros(I["At"].shape[1]), 1.0)
+        rows = []
+        for p in (100, 300):
+            h.rand_Y(p, 1)
+            h.slot_set(_lib.SLOT_U, np.random.default_rng(1).standard_normal((n, p)))
+            h.hess_bench(3)
+            ms = h.hess_bench(20)
+            st = h.stats()
+            tf = st.flops_per_hv / (ms * 1e-3) / 1e12
+            rows.append({"p": p, "ms_per_hv": ms, "flops_per_hv": st.flops_per_hv, "achieved_tflops": tf,
+                         "frac_of_dgemm_peak": tf / dgemm, "algorithmic_GBps": st.bytes_per_hv / (ms * 1e-3) / 1e9,
+                         "s_mode": int(st.s_mode), "a_mode": int(st.a_mode)})
+    out["bqp60_dense_path"] = {"n": n, "m": int(I["At"].shape[1]), "kernels": "K4 FP64 DMMA GEMM (gemm_f64.cu) x3 + A / At "
+                               "gathers over the dense pattern (affine.cu)", "rows": rows}
+    return out
 
 
 def main():

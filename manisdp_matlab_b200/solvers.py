@@ -76,7 +76,12 @@ def ManiSDP_onlyunitdiag(C, options=None):
     _say(o, f"SDP size: n = {n}, m = {n}")
     data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[], tr_seconds=0.0)
     t0 = time.perf_counter()
-    with _lib.Handle("onlyunitdiag", n, C_csc=C, device=o["device"]) as h:
+    # Multi-GPU (extension): options.world > 1 with options.rank / options.nccl_id runs the same loop on a
+    # column-sharded handle -- the trust-region solve on p/world columns per GPU, the outer-loop steps (eigen step, rank
+    # step, escape) redundantly and identically on every rank on the merged factor.  One process per GPU calls this.
+    world = int(o.get("world", 1))
+    with _lib.Handle("onlyunitdiag", n, C_csc=C, device=o["device"], rank=int(o.get("rank", 0)), world=world,
+                     nccl_id=o.get("nccl_id"), layout="cols" if world > 1 else "rows") as h:
         _init_point(h, o)
         data["setup_seconds"] = time.perf_counter() - t0
         staged = False
@@ -85,7 +90,11 @@ def ManiSDP_onlyunitdiag(C, options=None):
             data["fac_size"].append(h.p)
             if staged:
                 h.line_search()  # :40-42
+            if world > 1:
+                h.col_split()
             info = h.tr_solve(o["TR_maxiter"], o["TR_maxinner"], o["tolgradnorm"], o["use_graph"])  # :43
+            if world > 1:
+                h.col_merge()
             data["hv_count"] += info.hv_count
             data["tr_iters"] += info.iters
             data["tr_seconds"] += info.seconds
@@ -94,6 +103,7 @@ def ManiSDP_onlyunitdiag(C, options=None):
             k = h.kkt(int(o["delta"]), o["eig_tol"], 0)  # :45-51
             data["kkt_seconds"] = data.get("kkt_seconds", 0.0) + time.perf_counter() - t_k
             data["eig_iters_total"] = data.get("eig_iters_total", 0) + int(k.eig_iters)
+            data["eig_unconverged"] = data.get("eig_unconverged", 0) + (0 if k.eig_converged else 1)
             obj, dinf = k.obj, k.dinf
             p = h.p
             r, _ = h.rank_cut(o["theta"], apply=False)  # :52-54
@@ -124,7 +134,8 @@ def ManiSDP_onlyunitdiag(C, options=None):
         z = np.asarray(C.multiply(X).sum(axis=0)).ravel()
         S = C.toarray() - np.diag(z)
     data.update(X=X, S=S, z=z, dinf=dinf, gradnorm=gradnorm, time=time.perf_counter() - t0, Y=Y, iters=it, obj=obj,
-                lam_min=k.lam_min, lam_max=k.lam_max, eig_iters=k.eig_iters, eig_resid=k.eig_resid)
+                lam_min=k.lam_min, lam_max=k.lam_max, eig_iters=k.eig_iters, eig_resid=k.eig_resid,
+                eig_converged_last=int(k.eig_converged))
     if data["status"] == 0 and dinf > o["tol"]:
         data["status"] = 1
         _say(o, "Iteration maximum is reached!")
@@ -163,6 +174,10 @@ def _affine_driver(kind, At, b, c, K, options):
             gradnorm = info.gradnorm
             k = h.kkt(int(o["delta"]), o["eig_tol"], 1)  # residues, y <- y - sigma*Axb, eig(S)
             obj, gap, pinf, dinf = k.obj, k.gap, k.pinf, k.dinf
+            # Ritz values bound lambda_min from above: an eigen step that missed its residual test (after the engine's
+            # own two warm restarts) is counted, so a reported dinf can be audited (data['eig_unconverged'])
+            data["eig_unconverged"] = data.get("eig_unconverged", 0) + (0 if k.eig_converged else 1)
+            data["eig_iters_total"] = data.get("eig_iters_total", 0) + int(k.eig_iters)
             p = h.p
             r, _ = h.rank_cut(o["theta"], apply=False)
             _say(o, f"Iter {it}, obj:{obj:0.8f}, gap:{gap:0.1e}, pinf:{pinf:0.1e}, dinf:{dinf:0.1e}, "
@@ -210,7 +225,8 @@ def _affine_driver(kind, At, b, c, K, options):
         else:
             S = eS
     data.update(X=X, y=y, S=S, z=z, gap=gap, pinf=pinf, dinf=dinf, gradnorm=gradnorm, time=time.perf_counter() - t0,
-                Y=Y, iters=it, obj=obj, sigma=sigma, lam_min=k.lam_min, lam_max=k.lam_max, eig_iters=k.eig_iters)
+                Y=Y, iters=it, obj=obj, sigma=sigma, lam_min=k.lam_min, lam_max=k.lam_max, eig_iters=k.eig_iters,
+                eig_resid=k.eig_resid, eig_converged_last=int(k.eig_converged))
     if data["status"] == 0 and eta > o["tol"]:
         data["status"] = 1
         _say(o, "Iteration maximum is reached!")

@@ -46,8 +46,9 @@ def qs60():
     coe, sha = qs60_coefficients()
     At, b, c, K = g.qsmom(60, coe)
     t0 = time.perf_counter()
-    X, obj, data = ref.ManiSDP(At, b, c, K, dict(seed=0, tol=1e-8, theta=1e-2, tau1=0.02))
-    merge("qs_c_60_rng60_opt", dict(obj=obj, eta=max(data["gap"], data["pinf"], data["dinf"]), hv=data["hv_count"],
+    opts = dict(tol=1e-8, theta=1e-2, tau1=0.02, delta=6)
+    X, obj, data = ref.ManiSDP(At, b, c, K, dict(opts, seed=0))
+    merge("qs_c_60_rng60_opt", dict(options=opts, status=int(data["status"]), obj=obj, eta=max(data["gap"], data["pinf"], data["dinf"]), hv=data["hv_count"],
                                     iters=data["iters"], n=int(K["s"]), m=int(At.shape[1]), coe_sha256=sha,
                                     oracle_seconds=time.perf_counter() - t0))
 

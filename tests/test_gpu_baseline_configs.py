@@ -99,7 +99,8 @@ def test_config3_qs60_optimum_and_kkt():
     assert hashlib.sha256(coe.tobytes()).hexdigest() == gold["coe_sha256"]  # the same instance the oracle solved
     At, b, c, K = g.qsmom(60, coe)
     assert (int(K["s"]), At.shape[1]) == (1891, 1155402) == (gold["n"], gold["m"])
-    X, obj, data = ManiSDP(At, _dense_b(b), c, K, dict(verbose=False, tol=1e-8, theta=1e-2, tau1=0.02))
+    # example_qsphere.m:21-27 options + delta = 6 (example/settings.txt "qs"), as pinned by make_golden_large.py
+    X, obj, data = ManiSDP(At, _dense_b(b), c, K, dict(verbose=False, **gold["options"]))
     assert data["status"] == 0
     assert max(data["gap"], data["pinf"], data["dinf"]) <= 1e-8
     assert abs(obj - gold["obj"]) <= 1e-6 * abs(gold["obj"]), (obj, gold["obj"])

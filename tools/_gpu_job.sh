@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_maxcut.py -m gpu -q -k "lowdeg or wide_block" > gpurun_out/r2_pytest_c.log 2>&1; tail -8 gpurun_out/r2_pytest_c.log
-timeout 200 python tools/sweep_p.py torus 40,64 > gpurun_out/r2_sweep_torus_gw.jsonl 2>&1; cat gpurun_out/r2_sweep_torus_gw.jsonl
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_spmm_lowdeg -s 30 -c 1 -f -o gpurun_out/r2_lowdeg_torus_p64 python tools/sweep_p.py torus 64 > gpurun_out/ncu_lowdeg.log 2>&1; tail -2 gpurun_out/ncu_lowdeg.log
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_bm_ -s 100 -c 5 -f -o gpurun_out/r2_bm_er_p64 python tools/sweep_p.py er 64 > gpurun_out/ncu_bm.log 2>&1; tail -2 gpurun_out/ncu_bm.log
-timeout 900 python tools/run_configs.py er:1000000 --verbose --opts='{"p0": 256, "delta": 24}' > gpurun_out/r2_c5_er1e6_p256.log 2>&1; tail -12 gpurun_out/r2_c5_er1e6_p256.log
+nvidia-smi -L | head -3
+timeout 900 python -m pytest tests/test_gpu_sharded.py tests/test_gpu_maxcut.py tests/test_mex_gateway.py -m gpu -q -x -k "column or lowdeg or wide_block or gateway" > gpurun_out/r2_pytest_d.log 2>&1; tail -15 gpurun_out/r2_pytest_d.log
+timeout 200 python tools/sweep_p.py torus 40,64 > gpurun_out/r2_sweep_torus_gw_b.jsonl 2>&1; cat gpurun_out/r2_sweep_torus_gw_b.jsonl
+for g in er torus; do CHK_GRAPH=$g timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/check_colsharded.py 2>&1 | tail -4; done > gpurun_out/r2_colcheck_n2.log 2>&1; cat gpurun_out/r2_colcheck_n2.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; tail -c 3000 gpurun_out/r2_bench_n2.json; tail -5 gpurun_out/r2_bench_n2.err

@@ -74,6 +74,17 @@ def run(name, cpu):
         raise SystemExit(f"unknown config {name}")
     t_gen = time.perf_counter() - t0
     o = dict(opts, verbose="--verbose" in sys.argv)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:  # torchrun: config-5 family on a column-sharded handle, one rank per GPU
+        import torch
+        import torch.distributed as dist
+        rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        obj = [M._lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        o.update(world=world, rank=rank, device=local, nccl_id=obj[0], verbose=o["verbose"] and rank == 0)
     for a in sys.argv[1:]:
         if a.startswith("--opts="):  # option overrides as JSON, e.g. --opts='{"p0": 256, "delta": 24}'
             o.update(json.loads(a[len("--opts="):]))
@@ -87,7 +98,9 @@ def run(name, cpu):
                modes=[data.get("s_mode"), data.get("a_mode")], p_max=max(data["fac_size"]),
                kkt_seconds=data.get("kkt_seconds"), eig_iters=data.get("eig_iters_total"),
                setup_seconds=data.get("setup_seconds"), fac_size=data["fac_size"],
-               options={k: v for k, v in o.items() if k != "verbose"})
+               options={k: v for k, v in o.items() if k not in ("verbose", "nccl_id")}, n_gpus=world)
+    if world > 1 and int(os.environ["RANK"]) != 0:
+        return
     if cpu:
         t0 = time.perf_counter()
         Xc, objc, dc = call(ref, dict(opts, seed=0))
