@@ -10,7 +10,9 @@
 //     Each rank forms its partial row sums, one NCCL all-reduce of an n-vector (8 MB at n = 1e6, NVLS-reduced inside the
 //     switch) completes them, and a second light pass over the rank's columns applies them;
 //   * the tCG inner products are sums over all entries, all-reduced as scalars exactly like in the row-sharded path.
-// Per tCG iteration a rank moves 2 n-vectors + 7 scalars through the switch instead of the n x p factor.
+// Per tCG iteration a rank moves 3 n-vectors + 7 scalars through the switch, in three all-reduces (row sums of the
+// product; <mdelta, Hmdelta>; the update packet with the two row-sum vectors of the next direction), instead of the
+// n x p factor.
 //
 // A column-sharded handle is an ordinary single-GPU handle (h->world == 1: every rank holds every row) that is SPLIT for
 // the trust-region solve and MERGED for the outer-loop steps (KKT / eigen step / rank step / escape), which then run
@@ -20,6 +22,7 @@
 // While split only tr_solve / cost / get-set of the local slice are meaningful.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dist.h"
@@ -74,8 +77,11 @@ int msdp_col_init(manisdp_handle* h, const void* unique_id, int world, int rank)
   h->cworld = world > 1 ? world : 1;
   h->crank = world > 1 ? rank : 0;
   h->col_mode = 1;
+  if (const char* e = getenv("MANISDP_COL_GRAPH")) h->col_graph = atoi(e);
   CUDA_TRY(h, cudaMalloc((void**)&h->col_rowvec, (size_t)h->n * sizeof(double)));
   CUDA_TRY(h, cudaMemset(h->col_rowvec, 0, (size_t)h->n * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->col_pack, (size_t)(8 + 2 * h->n) * sizeof(double)));
+  CUDA_TRY(h, cudaMemset(h->col_pack, 0, (size_t)(8 + 2 * h->n) * sizeof(double)));
   if (h->cworld <= 1) return MANISDP_OK;
   if (!unique_id) return msdp_fail(h, MANISDP_E_ARG, "column-sharded handle needs nccl_unique_id");
   std::string why;
@@ -93,6 +99,8 @@ void msdp_col_destroy(manisdp_handle* h) {
   h->col_comm = nullptr;
   if (h->col_rowvec) cudaFree(h->col_rowvec);
   h->col_rowvec = nullptr;
+  if (h->col_pack) cudaFree(h->col_pack);
+  h->col_pack = nullptr;
 }
 
 static int col_allreduce(manisdp_handle* h, double* buf, int64_t count) {
@@ -391,6 +399,131 @@ int msdp_col_tcg_dir(manisdp_handle* h) {
   DISPATCH_GEOM(row_geom(h->ld), {
     const int nb = rows_grid(h, h->nloc, GS);
     k_col_dir_finish<GS, VPL><<<nb, MSDP_THREADS, 0, h->stream>>>(v, h->st, h->col_rowvec, h->nloc, ld);
+  });
+  KERNEL_CHECK(h);
+  return MANISDP_OK;
+}
+
+
+// ---- fused update pass of the split loop ---------------------------------------------------------------------------------
+// The update pass of tcg.cu (eta' = eta - a*mdelta, r' = r - a*Hmdelta and the inner products, tCG.m:192-241) in row
+// geometry, which also leaves the partial row sums the NEXT direction needs: mdelta' = P_Y(r' + beta*mdelta) subtracts
+// Y .* rowsum(Y .* (r' + beta*mdelta)) = Y .* (t1 + beta*t2) with t1 = rowsum(Y.*r'), t2 = rowsum(Y.*mdelta) -- both are
+// known before beta is.  pack = [6 scalars, 2 pad | t1 (n) | t2 (n)] travels through ONE all-reduce per iteration
+// (instead of a scalar packet and a separate n-vector for the direction).
+template <int GS, int VPL>
+__global__ void __launch_bounds__(MSDP_THREADS)
+    k_col_tcg_update(VecPtrs v, RtrState* st, double* partials, double* __restrict__ pack, int64_t nrows, int ld) {
+  __shared__ double sm[MSDP_NQ * 32];
+  if (st->stop != 0) return;
+  const int branch = st->branch, cur = st->eta_cur;
+  const double a = (branch != 0) ? st->tau : st->alpha;
+  const double* __restrict__ g = st->pt ? v.G1 : v.G0;
+  const double* __restrict__ Y = st->pt ? v.Y1 : v.Y0;
+  const double* __restrict__ eo = cur ? v.eta1 : v.eta0;
+  double* __restrict__ en = cur ? v.eta0 : v.eta1;
+  double* __restrict__ t1 = pack + 8;
+  double* __restrict__ t2 = pack + 8 + nrows;
+  const unsigned mask = group_mask<GS>();
+  const int gl = threadIdx.x % GS, nvec = ld / 2;
+  const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
+  double q[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; row < nrows; row += ngroups) {
+    const size_t base = (size_t)row * ld;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = gl + GS * k;
+      if (c < nvec) {
+        const size_t i = base + 2 * c;
+        const double2 e = ld2(eo + i), d = ld2(v.d + i), r = ld2(v.r + i), hd = ld2(v.Hd + i), gv = ld2(g + i);
+        double2 n;
+        n.x = e.x - a * d.x;  // tCG.m:192 / :215
+        n.y = e.y - a * d.y;
+        st2(en + i, n);
+        if (branch != 0) {
+          const double hx = (r.x - gv.x) - a * hd.x, hy = (r.y - gv.y) - a * hd.y;  // Heta - tau*Hmdelta (:196)
+          q[0] += n.x * gv.x + n.y * gv.y;
+          q[1] += n.x * hx + n.y * hy;
+          q[2] += n.x * n.x + n.y * n.y;
+        } else {
+          double2 rn;
+          rn.x = r.x - a * hd.x;  // :238
+          rn.y = r.y - a * hd.y;
+          st2(v.r + i, rn);
+          q[0] += n.x * gv.x + n.y * gv.y;
+          q[1] += n.x * (rn.x - gv.x) + n.y * (rn.y - gv.y);
+          q[2] += rn.x * rn.x + rn.y * rn.y;
+          q[3] += n.x * n.x + n.y * n.y;
+          const double2 y = ld2(Y + i);
+          s1 += y.x * rn.x + y.y * rn.y;
+          s2 += y.x * d.x + y.y * d.y;
+        }
+      }
+    }
+    if (branch == 0) {
+      s1 = group_sum<GS>(s1, mask);
+      s2 = group_sum<GS>(s2, mask);
+      if (gl == 0) {
+        t1[row] = s1;
+        t2[row] = s2;
+      }
+    }
+  }
+  double tot[6];
+  if (grid_sum_last<6>(q, partials, &st->ticket, sm, tot)) {
+    if (threadIdx.x == 0)
+      for (int k = 0; k < 6; ++k) pack[k] = tot[k];
+  }
+}
+__global__ void k_col_after_update(RtrState* st, const double* pack, cudaGraphConditionalHandle cond, int use_cond) {
+  if (st->stop != 0) return;
+  tcg_after_update(st, pack, cond, use_cond);
+}
+// mdelta = (r + beta*mdelta) - Y .* (t1 + beta*t2)   (tCG.m:273,283)
+template <int GS, int VPL>
+__global__ void __launch_bounds__(MSDP_THREADS)
+    k_col_tcg_dir(VecPtrs v, RtrState* st, const double* __restrict__ pack, int64_t nrows, int ld) {
+  if (st->stop != 0) return;
+  const double beta = st->beta;
+  const double* __restrict__ Y = st->pt ? v.Y1 : v.Y0;
+  const double* __restrict__ t1 = pack + 8;
+  const double* __restrict__ t2 = pack + 8 + nrows;
+  const int gl = threadIdx.x % GS, nvec = ld / 2;
+  const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; row < nrows; row += ngroups) {
+    const size_t base = (size_t)row * ld;
+    const double dot = t1[row] + beta * t2[row];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = gl + GS * k;
+      if (c < nvec) {
+        const size_t i = base + 2 * c;
+        const double2 r = ld2(v.r + i), d = ld2(v.d + i), y = ld2(Y + i);
+        double2 dn;
+        dn.x = (r.x + beta * d.x) - y.x * dot;
+        dn.y = (r.y + beta * d.y) - y.y * dot;
+        st2(v.d + i, dn);
+      }
+    }
+  }
+}
+
+// update pass + ONE all-reduce + scalar logic + new direction of one split tCG iteration
+int msdp_col_tcg_update_dir(manisdp_handle* h, cudaGraphConditionalHandle cond, int use_cond) {
+  const VecPtrs v = msdp_vecptrs(h);
+  const int ld = (int)h->ld;
+  DISPATCH_GEOM(row_geom(h->ld), {
+    const int nb = rows_grid(h, h->nloc, GS);
+    k_col_tcg_update<GS, VPL><<<nb, MSDP_THREADS, 0, h->stream>>>(v, h->st, h->partials, h->col_pack, h->nloc, ld);
+  });
+  KERNEL_CHECK(h);
+  MSDP_TRY(col_allreduce(h, h->col_pack, 8 + 2 * h->nloc));
+  k_col_after_update<<<1, 1, 0, h->stream>>>(h->st, h->col_pack, cond, use_cond);
+  KERNEL_CHECK(h);
+  DISPATCH_GEOM(row_geom(h->ld), {
+    const int nb = rows_grid(h, h->nloc, GS);
+    k_col_tcg_dir<GS, VPL><<<nb, MSDP_THREADS, 0, h->stream>>>(v, h->st, h->col_pack, h->nloc, ld);
   });
   KERNEL_CHECK(h);
   return MANISDP_OK;

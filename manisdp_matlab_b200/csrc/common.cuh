@@ -172,9 +172,11 @@ struct manisdp_handle {
   // column-sharded layout (colshard.cu): every rank holds all rows; split = only pl = ceil(p/G) columns of the factor
   int col_mode = 0, cworld = 1, crank = 0;
   int col_split = 0;                    // 1 between manisdp_col_split and manisdp_col_merge
+  int col_graph = 0;                    // world > 1: capture the split tCG loop (with its all-reduces) in a CUDA graph
   int col_pfull = 0;                    // width of the factor at the last split
   void* col_comm = nullptr;             // ncclComm_t
   double* col_rowvec = nullptr;         // n: per-row partial sums on their way through the all-reduce
+  double* col_pack = nullptr;           // 8 + 2n: update packet [6 scalars, pad | rowsum(Y.*r') | rowsum(Y.*mdelta)]
   std::string err;
 };
 

@@ -10,7 +10,7 @@ VecPtrs msdp_vecptrs(const manisdp_handle* h);
 // tcg.cu
 int msdp_launch_tcg_init(manisdp_handle* h);
 int msdp_launch_tcg_update(manisdp_handle* h, cudaGraphConditionalHandle cond, int use_cond, int defer);
-int msdp_launch_tcg_after_update_scalar(manisdp_handle* h);
+int msdp_launch_tcg_after_update_scalar(manisdp_handle* h, cudaGraphConditionalHandle cond = 0, int use_cond = 0);
 int msdp_launch_tcg_dir(manisdp_handle* h);
 int msdp_launch_retract(manisdp_handle* h, const double* Y, const double* eta, double* dst, int from_state);
 int msdp_launch_project(manisdp_handle* h, const double* Y, const double* src, double* dst);
@@ -54,5 +54,6 @@ int msdp_col_hess(manisdp_handle* h, const double* D, double* Hout, int from_sta
 int msdp_col_costgrad(manisdp_handle* h, int buf);  // leaves the all-reduced (sum eG, |G|^2) in st->tmp[0..1]
 int msdp_col_retract(manisdp_handle* h);
 int msdp_col_tcg_dir(manisdp_handle* h);
+int msdp_col_tcg_update_dir(manisdp_handle* h, cudaGraphConditionalHandle cond, int use_cond);
 int msdp_col_allreduce_tmp(manisdp_handle* h, int count);
 int msdp_col_cg_scalar(manisdp_handle* h, int cg_mode);  // scalar tail of a cost+grad call (CG_* modes)

@@ -56,12 +56,7 @@ static int tcg_hv(manisdp_handle* h) {
 
 static int tcg_iteration(manisdp_handle* h, cudaGraphConditionalHandle cond, int use_cond) {
   MSDP_TRY(tcg_hv(h));
-  if (h->col_split) {
-    MSDP_TRY(msdp_launch_tcg_update(h, cond, 0, 1));
-    MSDP_TRY(msdp_col_allreduce_tmp(h, 6));
-    MSDP_TRY(msdp_launch_tcg_after_update_scalar(h));
-    return msdp_col_tcg_dir(h);
-  }
+  if (h->col_split) return msdp_col_tcg_update_dir(h, cond, use_cond);
   if (h->world > 1) {
     MSDP_TRY(msdp_launch_tcg_update(h, cond, 0, 1));
     MSDP_TRY(msdp_dist_allreduce_tmp(h, 6));
@@ -185,7 +180,10 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
   if (opt.rho_regularization <= 0) opt.rho_regularization = 1e3;
   if (opt.Delta_bar <= 0) opt.Delta_bar = typicaldist;
   if (opt.Delta0 <= 0) opt.Delta0 = opt.Delta_bar / 8.0;
-  const int use_graph = (opt.use_graph != 0) && (h->world <= 1) && !h->col_split;
+  // column-split handles: the NCCL all-reduces of the loop are captured into the graph (and into the body of its WHILE
+  // node) like the kernels around them -- opt-in for world > 1 (MANISDP_COL_GRAPH=1) until it has been measured
+  const bool col_graph_ok = !h->col_split || h->cworld <= 1 || h->col_graph;
+  const int use_graph = (opt.use_graph != 0) && (h->world <= 1) && col_graph_ok;
   h->y_version++;
 
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));

@@ -254,9 +254,9 @@ __global__ void __launch_bounds__(MSDP_THREADS)
   }
 }
 
-__global__ void k_tcg_after_update_scalar(RtrState* st) {
+__global__ void k_tcg_after_update_scalar(RtrState* st, cudaGraphConditionalHandle cond, int use_cond) {
   if (st->stop != 0) return;
-  tcg_after_update(st, st->tmp, 0, 0);
+  tcg_after_update(st, st->tmp, cond, use_cond);
 }
 
 // ---- host launchers -------------------------------------------------------------------------------------------------
@@ -310,8 +310,8 @@ int msdp_launch_tcg_update(manisdp_handle* h, cudaGraphConditionalHandle cond, i
   return MANISDP_OK;
 }
 
-int msdp_launch_tcg_after_update_scalar(manisdp_handle* h) {
-  k_tcg_after_update_scalar<<<1, 1, 0, h->stream>>>(h->st);
+int msdp_launch_tcg_after_update_scalar(manisdp_handle* h, cudaGraphConditionalHandle cond, int use_cond) {
+  k_tcg_after_update_scalar<<<1, 1, 0, h->stream>>>(h->st, cond, use_cond);
   KERNEL_CHECK(h);
   return MANISDP_OK;
 }
