@@ -274,10 +274,12 @@ def run_ours(args, rank, world):
     Y0p = torch.from_numpy(np.ascontiguousarray(Y0)).pin_memory().numpy()
     out_host = torch.empty(Y0.shape, dtype=torch.float64).pin_memory().numpy()
     h.set_Y(Y0p)
-    use_graph = 0 if world > 1 else args.graph
+    # N > 1: the column-split loop can run as a CUDA graph too (its all-reduces captured), opt-in: MANISDP_COL_GRAPH=1
+    use_graph = args.graph if (world == 1 or (layout == "cols" and os.environ.get("MANISDP_COL_GRAPH") == "1")) else 0
 
     def step(hh=None):
-        return (hh or h).tr_solve(maxiter=1, maxinner=args.inner, tolgradnorm=1e-12, use_graph=use_graph)
+        ug = use_graph if (hh is None or hh is h) else 0
+        return (hh or h).tr_solve(maxiter=1, maxinner=args.inner, tolgradnorm=1e-12, use_graph=ug)
 
     def timed(hh, steps):
         barrier()

@@ -194,7 +194,11 @@ int manisdp_tr_log(manisdp_t *h, manisdp_tr_iter *buf, int32_t cap, int32_t *cou
 /* ---- outer-loop pieces ------------------------------------------------------------------------------------- */
 /* KKT residues + dual update y <- y - sigma*(A(X) - b) + the `delta` smallest eigenpairs of S (device LOBPCG) and
  * lambda_max (Lanczos).  The eigenvectors stay on the device for manisdp_escape.
- * update_dual = 0 evaluates the residues without changing y. */
+ * update_dual = 0 evaluates the residues without changing y.
+ * eig_tol: residual tolerance of the eigen step relative to 1 + lambda_max.  0: 1e-9.  Negative: ADAPTIVE, |eig_tol| is
+ * the caller's KKT tolerance -- the tolerance follows the previous dinf (1e-2 * dinf_prev in [1e-9, 1e-5]) and the block is
+ * continued to 1e-9 whenever the new dinf comes within 100x of the KKT tolerance, so an accepted dinf < tol rests on
+ * the tight tolerance (what the drivers pass by default). */
 int manisdp_kkt(manisdp_t *h, int32_t delta, double eig_tol, int32_t update_dual, manisdp_kkt_info *out);
 /* eigenvalues (ascending, count = min(cap, delta of the last kkt call)) and optionally vectors (n x count, ROWS) */
 int manisdp_get_eigs(manisdp_t *h, double *vals, double *vecs, int32_t cap);

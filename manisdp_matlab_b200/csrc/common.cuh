@@ -172,6 +172,8 @@ struct manisdp_handle {
   // column-sharded layout (colshard.cu): every rank holds all rows; split = only pl = ceil(p/G) columns of the factor
   int col_mode = 0, cworld = 1, crank = 0;
   int col_split = 0;                    // 1 between manisdp_col_split and manisdp_col_merge
+  double last_dinf = 1e-3;              // dinf of the previous kkt call (adaptive eigen-step tolerance)
+  int last_numinner = 0;                // inner iterations of the previous TR iteration (chunking of the stream loop)
   int col_graph = 0;                    // world > 1: capture the split tCG loop (with its all-reduces) in a CUDA graph
   int col_pfull = 0;                    // width of the factor at the last split
   void* col_comm = nullptr;             // ncclComm_t

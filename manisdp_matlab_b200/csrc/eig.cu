@@ -634,7 +634,17 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
   // the LOBPCG block is delta + 4 columns; its kernels (k_resid, k_combine) are laid out for blocks of <= 64 columns
   if (delta > 60)
     return msdp_fail(h, MANISDP_E_ARG, "kkt: options.delta > 60 is not supported (LOBPCG block of delta + 4 <= 64 columns)");
-  if (eig_tol <= 0) eig_tol = 1e-9;
+  // eig_tol < 0: ADAPTIVE accuracy of the eigen step, |eig_tol| = the driver's KKT tolerance.  Far from convergence the
+  // escape directions and dinf only need a few digits, so the residual tolerance follows the previous dinf
+  // (1e-2 * dinf_prev, clamped to [1e-9, 1e-5]); whenever the resulting dinf comes within 100x of the KKT tolerance the
+  // block is continued (warm) to the tight tolerance 1e-9 before anything is reported, so an accepted "dinf < tol" always
+  // rests on the same accuracy as the fixed-tolerance mode.  (The reference's eig() is exact: ManiSDP_unitdiag.m:68.)
+  double kkt_tol = 0.0;
+  if (eig_tol < 0) {
+    kkt_tol = -eig_tol;
+    eig_tol = std::min(1e-5, std::max(1e-9, 1e-2 * h->last_dinf));
+  }
+  if (eig_tol == 0) eig_tol = 1e-9;
   // residues + dual slack operator of the driver
   if (h->kind == MANISDP_ONLYUNITDIAG) {
     // z = sum(C.*X) = eG of the cost kernel; obj = sum(z); S = C - diag(z)  (ManiSDP_onlyunitdiag.m:45-49)
@@ -678,9 +688,17 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
     // more, and tell the caller (eig_converged) if the residual test is still not met.
     bool conv = false;
     MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_abs, 0.0, 1500, warm ? 1 : 0, vals, &resid, &iters, &conv));
+    double tol_now = tol_abs;
+    if (kkt_tol > 0 && eig_tol > 1e-9 && !vals.empty() &&
+        std::max(0.0, -vals[0]) / (1.0 + lam_max) < 100.0 * kkt_tol) {  // close to acceptance: tighten before reporting
+      tol_now = 1e-9 * (1.0 + fabs(lam_max));
+      int it3 = 0;
+      MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_now, 0.0, 1500, 1, vals, &resid, &it3, &conv));
+      iters += it3;
+    }
     for (int attempt = 0; attempt < 2 && !conv; ++attempt) {
       int it3 = 0;
-      MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_abs, 0.0, 1500, 1, vals, &resid, &it3, &conv));
+      MSDP_TRY(lobpcg(h, st.lo, delta, 0, tol_now, 0.0, 1500, 1, vals, &resid, &it3, &conv));
       iters += it3;
     }
     converged = conv ? 1 : 0;
@@ -707,6 +725,7 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
   out->lam_min = vals.empty() ? 0.0 : vals[0];
   out->lam_max = lam_max;
   out->dinf = std::max(0.0, -out->lam_min) / (1.0 + lam_max);  // ManiSDP_onlyunitdiag.m:51
+  h->last_dinf = out->dinf;
   out->nneg = std::min(nneg, delta);
   out->eig_iters = iters;
   out->eig_resid = resid;

@@ -251,6 +251,10 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
       const bool cheap_stop = (h->world <= 1) && !col_comm;
       const int chunk_cap = cheap_stop ? 32 : ((col_comm || msdp_peer_gather_ok(h)) ? 4 : 1);
       int chunk = cheap_stop ? 4 : ((col_comm || msdp_peer_gather_ok(h)) ? 2 : 1);
+      // column-sharded: consecutive TR iterations tend to need similar numbers of inner iterations -- issue as many
+      // as the previous solve used (minus one) before the first look at the stop flag, then continue one at a time
+      if (col_comm && h->last_numinner > 2) chunk = h->last_numinner - 1;
+      bool first_chunk = true;
       while (!done && issued < opt.maxinner) {
         int c = chunk;
         if (c > opt.maxinner - issued) c = opt.maxinner - issued;
@@ -260,12 +264,18 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
                                     h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         done = (h->st_host->stop != 0);
-        if (chunk < chunk_cap) chunk *= 2;
+        if (col_comm && first_chunk) {
+          chunk = 1;
+          first_chunk = false;
+        } else if (chunk < chunk_cap) {
+          chunk *= 2;
+        }
       }
       MSDP_TRY(tr_tail(h));
     }
     MSDP_TRY(msdp_sync_state(h));
     if (use_graph) h->launches += h->graph_l_fixed + h->graph_l_body * (int64_t)sh->j;
+    h->last_numinner = sh->j;
     ++k;
     naccepted += sh->accepted;
     rec.iter = k;

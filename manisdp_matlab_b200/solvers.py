@@ -47,7 +47,7 @@ def _opts(kind, options):
     o.setdefault("seed", 0)
     o.setdefault("verbose", True)
     o.setdefault("use_graph", 1)
-    o.setdefault("eig_tol", 0.0)
+    o.setdefault("eig_tol", 0.0)  # 0: adaptive eigen-step accuracy keyed to options.tol (include/manisdp_b200.h: manisdp_kkt)
     o.setdefault("device", 0)
     return o
 
@@ -100,7 +100,7 @@ def ManiSDP_onlyunitdiag(C, options=None):
             data["tr_seconds"] += info.seconds
             gradnorm = info.gradnorm
             t_k = time.perf_counter()
-            k = h.kkt(int(o["delta"]), o["eig_tol"], 0)  # :45-51
+            k = h.kkt(int(o["delta"]), o["eig_tol"] if o["eig_tol"] > 0 else -float(o["tol"]), 0)  # :45-51
             data["kkt_seconds"] = data.get("kkt_seconds", 0.0) + time.perf_counter() - t_k
             data["eig_iters_total"] = data.get("eig_iters_total", 0) + int(k.eig_iters)
             data["eig_unconverged"] = data.get("eig_unconverged", 0) + (0 if k.eig_converged else 1)
@@ -159,27 +159,36 @@ def _affine_driver(kind, At, b, c, K, options):
     check_every, check_after = (50, 100) if kind == "unitdiag" else (20, 50)
     t0 = time.perf_counter()
     gap0 = pinf0 = dinf0 = None
+    phase = dict(create=0.0, line_search=0.0, tr_solve=0.0, kkt=0.0, rank=0.0, escape=0.0)  # wall seconds per phase
+
+    def timed(name, fn, *a):
+        t1 = time.perf_counter()
+        r_ = fn(*a)
+        phase[name] += time.perf_counter() - t1
+        return r_
+
     with _lib.Handle(kind, n, At=At, b=bd, c=c, device=o["device"], force_mode=int(o.get("force_mode", 0))) as h:
         h.set_dual(np.zeros(m), sigma)
         _init_point(h, o)
+        phase["create"] = time.perf_counter() - t0
         staged = False
         for it in range(1, int(o["AL_maxiter"]) + 1):
             data["fac_size"].append(h.p)
             if staged:
-                h.line_search()
-            info = h.tr_solve(o["TR_maxiter"], o["TR_maxinner"], o["tolgradnorm"], o["use_graph"])
+                timed("line_search", h.line_search)
+            info = timed("tr_solve", h.tr_solve, o["TR_maxiter"], o["TR_maxinner"], o["tolgradnorm"], o["use_graph"])
             data["hv_count"] += info.hv_count
             data["tr_iters"] += info.iters
             data["tr_seconds"] += info.seconds
             gradnorm = info.gradnorm
-            k = h.kkt(int(o["delta"]), o["eig_tol"], 1)  # residues, y <- y - sigma*Axb, eig(S)
+            k = timed("kkt", h.kkt, int(o["delta"]), o["eig_tol"] if o["eig_tol"] > 0 else -float(o["tol"]), 1)  # residues, y <- y - sigma*Axb, eig(S)
             obj, gap, pinf, dinf = k.obj, k.gap, k.pinf, k.dinf
             # Ritz values bound lambda_min from above: an eigen step that missed its residual test (after the engine's
             # own two warm restarts) is counted, so a reported dinf can be audited (data['eig_unconverged'])
             data["eig_unconverged"] = data.get("eig_unconverged", 0) + (0 if k.eig_converged else 1)
             data["eig_iters_total"] = data.get("eig_iters_total", 0) + int(k.eig_iters)
             p = h.p
-            r, _ = h.rank_cut(o["theta"], apply=False)
+            r, _ = timed("rank", h.rank_cut, o["theta"], False)
             _say(o, f"Iter {it}, obj:{obj:0.8f}, gap:{gap:0.1e}, pinf:{pinf:0.1e}, dinf:{dinf:0.1e}, "
                     f"gradnorm:{gradnorm:0.1e}, r:{r}, p:{p}, sigma:{sigma:0.3f}, time:{time.perf_counter()-t0:0.2f}s")
             eta = max(gap, pinf, dinf)
@@ -195,12 +204,12 @@ def _affine_driver(kind, At, b, c, K, options):
             if it == int(o["AL_maxiter"]):
                 break
             if r <= p - 1:
-                h.rank_cut(o["theta"], apply=True)
+                timed("rank", h.rank_cut, o["theta"], True)
             nne = min(k.nneg, int(o["delta"]))
             if kind == "unitdiag":
                 nne = max(nne, 1)  # ManiSDP_unitdiag.m:97 (the other two have no lower bound)
             staged = int(o["line_search"]) == 1
-            h.escape(nne, o["alpha"], int(o["line_search"]))
+            timed("escape", h.escape, nne, o["alpha"], int(o["line_search"]))
             if pinf < o["tau1"] * gradnorm:  # ManiSDP_unitdiag.m:108-112
                 sigma = max(sigma / gama, o["sigma_min"])
             elif pinf > o["tau2"] * gradnorm:
@@ -211,6 +220,7 @@ def _affine_driver(kind, At, b, c, K, options):
         st = h.stats()
         data["launches"] = st.launches_total
         data["s_mode"], data["a_mode"] = st.s_mode, st.a_mode
+        data["phase_seconds"] = phase
     X = S = z = None
     if n <= DENSE_OUTPUT_MAX_N:
         X = Y @ Y.T

@@ -49,7 +49,9 @@ for iter = 1:options.AL_maxiter
     info = manisdp_mex('tr_solve', h, tropts);
     data.hv_count = data.hv_count + info.hv_count;
     gradnorm = info.gradnorm;
-    k = manisdp_mex('kkt', h, options.delta, options.eig_tol, double(kind > 0));
+    eig_tol = options.eig_tol;
+    if eig_tol <= 0; eig_tol = -options.tol; end   % adaptive eigen-step accuracy keyed to options.tol (manisdp_b200.h)
+    k = manisdp_mex('kkt', h, options.delta, eig_tol, double(kind > 0));
     obj = k.obj; dinf = k.dinf; gap = k.gap; pinf = k.pinf;
     r = manisdp_mex('rank_cut', h, options.theta, 0);
     if kind == 0

@@ -20,6 +20,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, deg, p = int(os.environ.get("CHK_N", 20011)), 12, int(os.environ.get("CHK_P", 18))
+    UG = int(os.environ.get("CHK_USE_GRAPH", 0))  # 1 with MANISDP_COL_GRAPH=1: the split loop as a CUDA graph
     if os.environ.get("CHK_GRAPH", "er") == "torus":
         n, ei, ej, w = P.synthetic_torus(int(round(n ** 0.5)), seed=3)
     else:
@@ -44,7 +45,7 @@ def main():
     f = h.cost()
     g, gn = h.grad()
     hv = h.hess(Up[:, sl])
-    info = h.tr_solve(maxiter=8, maxinner=20, tolgradnorm=1e-9, use_graph=0)
+    info = h.tr_solve(maxiter=8, maxinner=20, tolgradnorm=1e-9, use_graph=UG)
     log = [(r.cost, r.gradnorm, r.numinner, r.accepted, r.stop_inner) for r in h.tr_log()]
     h.col_merge()
     assert h.p == pfull
@@ -53,7 +54,7 @@ def main():
     r_cut, _ = h.rank_cut(1e-1, apply=False)
     h.escape(max(1, min(int(k.nneg), 4)), 0.5, 0)
     h.col_split()  # second phase: a wider factor (reallocation) through the same handle
-    info2 = h.tr_solve(maxiter=3, maxinner=10, tolgradnorm=1e-9, use_graph=0)
+    info2 = h.tr_solve(maxiter=3, maxinner=10, tolgradnorm=1e-9, use_graph=UG)
     h.col_merge()
     Ym2 = h.get_Y()
     h.close()
@@ -70,14 +71,14 @@ def main():
             f1 = h1.cost()
             g1, gn1 = h1.grad()
             hv1 = h1.hess(Up)
-            info1 = h1.tr_solve(maxiter=8, maxinner=20, tolgradnorm=1e-9, use_graph=0)
+            info1 = h1.tr_solve(maxiter=8, maxinner=20, tolgradnorm=1e-9, use_graph=UG)
             log1 = [(r.cost, r.gradnorm, r.numinner, r.accepted, r.stop_inner) for r in h1.tr_log()]
             Y1 = h1.get_Y()
             k1 = h1.kkt(4, 1e-8, 0)
             r1c, _ = h1.rank_cut(1e-1, apply=False)
             h1.escape(max(1, min(int(k1.nneg), 4)), 0.5, 0)
             p_esc = h1.p
-            info21 = h1.tr_solve(maxiter=3, maxinner=10, tolgradnorm=1e-9, use_graph=0)
+            info21 = h1.tr_solve(maxiter=3, maxinner=10, tolgradnorm=1e-9, use_graph=UG)
         rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
         same_path = [(a[2], a[3], a[4]) for a in log] == [(a[2], a[3], a[4]) for a in log1]
         errc = max(abs(a[0] - b[0]) / abs(b[0]) for a, b in zip(log, log1))

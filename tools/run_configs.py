@@ -97,7 +97,7 @@ def run(name, cpu):
                status=data["status"], launches=int(data.get("launches", 0)), gen_seconds=t_gen,
                modes=[data.get("s_mode"), data.get("a_mode")], p_max=max(data["fac_size"]),
                kkt_seconds=data.get("kkt_seconds"), eig_iters=data.get("eig_iters_total"),
-               setup_seconds=data.get("setup_seconds"), fac_size=data["fac_size"],
+               setup_seconds=data.get("setup_seconds"), fac_size=data["fac_size"], phase_seconds=data.get("phase_seconds"),
                options={k: v for k, v in o.items() if k not in ("verbose", "nccl_id")}, n_gpus=world)
     if world > 1 and int(os.environ["RANK"]) != 0:
         return
