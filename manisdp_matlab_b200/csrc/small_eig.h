@@ -5,13 +5,78 @@
 #pragma once
 #include <math.h>
 #include <algorithm>
+#include <thread>
 #include <vector>
+
+// The O(n^3) loops below are unit-stride over columns; MSDP_SIMD lets the host compiler vectorise their reductions
+// (build.py passes -fopenmp-simd) and MSDP_EIG_CLONES builds an AVX2/FMA clone next to the baseline x86-64 one, chosen at
+// load time by the CPU (the library is built in one container and run on another).
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(__CUDA_ARCH__)
+#define MSDP_EIG_CLONES __attribute__((target_clones("arch=haswell", "default")))
+#else
+#define MSDP_EIG_CLONES
+#endif
+#define MSDP_DO_PRAGMA(x) _Pragma(#x)
+#define MSDP_SIMD_SUM(var) MSDP_DO_PRAGMA(omp simd reduction(+ : var))
+#define MSDP_SIMD _Pragma("omp simd")
+
+struct EigRotation {
+  int i;
+  double c, s;
+};
+
+// Apply the recorded QL rotations to rows [k0, k1) of the column-major n x n matrix V (column i and i + 1 per rotation)
+MSDP_EIG_CLONES inline void sym_eig_apply_rotations(double* V, int n, const std::vector<EigRotation>& rot, int k0, int k1) {
+  // Row blocks of RB rows go through the WHOLE rotation sequence (their RB x n slice stays in L1).  Inside a QL sweep the
+  // rotations walk down the columns, (i, i+1) then (i-1, i): the updated column i is carried in registers to the next
+  // rotation instead of going through a store -> load round trip.
+  constexpr int RB = 32;
+  const size_t nrot = rot.size();
+  for (int kb = k0; kb < k1; kb += RB) {
+    const int kr = std::min(RB, k1 - kb);
+    double carry[RB];
+    size_t t = 0;
+    while (t < nrot) {
+      int i = rot[t].i;
+      {
+        const double* __restrict__ b0 = V + (size_t)(i + 1) * n + kb;
+        for (int k = 0; k < kr; ++k) carry[k] = b0[k];
+      }
+      while (true) {
+        double* __restrict__ a = V + (size_t)i * n + kb;
+        double* __restrict__ b = V + (size_t)(i + 1) * n + kb;
+        const double c = rot[t].c, s = rot[t].s;
+        if (kr == RB) {
+          MSDP_SIMD
+          for (int k = 0; k < RB; ++k) {
+            const double av = a[k], h = carry[k];
+            b[k] = s * av + c * h;
+            carry[k] = c * av - s * h;
+          }
+        } else {
+          for (int k = 0; k < kr; ++k) {
+            const double av = a[k], h = carry[k];
+            b[k] = s * av + c * h;
+            carry[k] = c * av - s * h;
+          }
+        }
+        ++t;
+        if (t < nrot && rot[t].i == i - 1) {
+          --i;
+          continue;
+        }
+        for (int k = 0; k < kr; ++k) a[k] = carry[k];
+        break;
+      }
+    }
+  }
+}
 
 // A: n x n symmetric, row-major.  On return V (n x n, row-major) holds eigenvectors in COLUMNS and w the eigenvalues in
 // ascending order.  Returns false if QL fails to converge (never observed; 60 sweeps per eigenvalue allowed).
 // want_vectors = false: eigenvalues only (skips the accumulation of the Householder reflectors and the rotation
 // updates, ~5x cheaper); V is then scratch.
-inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& V,
+MSDP_EIG_CLONES inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& V,
                     bool want_vectors = true) {
   V = A;
   w.assign(n, 0.0);
@@ -48,9 +113,17 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
         f = w[j];
         v(j, i) = f;
         g = e[j] + v(j, j) * f;
-        for (int k = j + 1; k <= i - 1; ++k) {
-          g += v(k, j) * w[k];
-          e[k] += v(k, j) * f;
+        {
+          const double* __restrict__ col = &v(0, j);
+          double* __restrict__ ee = e.data();
+          const double* __restrict__ ww = w.data();
+          double gs = 0.0;
+          MSDP_SIMD_SUM(gs)
+          for (int k = j + 1; k <= i - 1; ++k) {
+            gs += col[k] * ww[k];
+            ee[k] += col[k] * f;
+          }
+          g += gs;
         }
         e[j] = g;
       }
@@ -64,7 +137,13 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
       for (int j = 0; j < i; ++j) {
         f = w[j];
         g = e[j];
-        for (int k = j; k <= i - 1; ++k) v(k, j) -= (f * e[k] + g * w[k]);
+        {
+          double* __restrict__ col = &v(0, j);
+          const double* __restrict__ ee = e.data();
+          const double* __restrict__ ww = w.data();
+          MSDP_SIMD
+          for (int k = j; k <= i - 1; ++k) col[k] -= (f * ee[k] + g * ww[k]);
+        }
         w[j] = v(i - 1, j);
         v(i, j) = 0.0;
       }
@@ -80,8 +159,13 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
       for (int k = 0; k <= i; ++k) w[k] = v(k, i + 1) / hh;
       for (int j = 0; j <= i; ++j) {
         double g = 0.0;
-        for (int k = 0; k <= i; ++k) g += v(k, i + 1) * v(k, j);
-        for (int k = 0; k <= i; ++k) v(k, j) -= g * w[k];
+        const double* __restrict__ ci = &v(0, i + 1);
+        double* __restrict__ cj = &v(0, j);
+        const double* __restrict__ ww = w.data();
+        MSDP_SIMD_SUM(g)
+        for (int k = 0; k <= i; ++k) g += ci[k] * cj[k];
+        MSDP_SIMD
+        for (int k = 0; k <= i; ++k) cj[k] -= g * ww[k];
       }
     }
     for (int k = 0; k <= i; ++k) v(k, i + 1) = 0.0;
@@ -97,6 +181,10 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
   e[n - 1] = 0.0;
   double f = 0.0, tst1 = 0.0;
   const double eps = 2.220446049250313e-16;
+  // the rotations of the QL sweeps are recorded and applied to the accumulated transformation afterwards, rows split over
+  // a few host threads (every row of V sees the same sequence of rotations, independently of the other rows)
+  std::vector<EigRotation> rot;
+  if (want_vectors) rot.reserve((size_t)n * (size_t)n);
   for (int l = 0; l < n; ++l) {
     tst1 = std::max(tst1, fabs(w[l]) + fabs(e[l]));
     int m = l;
@@ -135,11 +223,7 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
           c = p / r;
           p = c * w[i] - s * g;
           w[i + 1] = h + s * (c * g + s * w[i]);
-          for (int k = 0; want_vectors && k < n; ++k) {
-            h = v(k, i + 1);
-            v(k, i + 1) = s * v(k, i) + c * h;
-            v(k, i) = c * v(k, i) - s * h;
-          }
+          if (want_vectors) rot.push_back(EigRotation{i, c, s});
         }
         p = -s * s2 * c3 * el1 * e[l] / dl1;
         e[l] = s * p;
@@ -148,6 +232,26 @@ inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w,
     }
     w[l] = w[l] + f;
     e[l] = 0.0;
+  }
+  if (want_vectors && !rot.empty()) {
+    int T = 1;
+    if ((size_t)n * rot.size() > (size_t)4000000) {
+      const unsigned hw = std::thread::hardware_concurrency();
+      T = (int)std::max(1u, std::min(8u, hw / 2));
+      T = std::min(T, std::max(1, n / 32));
+    }
+    if (T <= 1) {
+      sym_eig_apply_rotations(V.data(), n, rot, 0, n);
+    } else {
+      std::vector<std::thread> th;
+      const int chunk = (n + T - 1) / T;
+      for (int t = 1; t < T; ++t) {
+        const int k0 = std::min(n, t * chunk), k1 = std::min(n, k0 + chunk);
+        th.emplace_back([&, k0, k1]() { sym_eig_apply_rotations(V.data(), n, rot, k0, k1); });
+      }
+      sym_eig_apply_rotations(V.data(), n, rot, 0, std::min(n, chunk));
+      for (auto& t : th) t.join();
+    }
   }
   // --- sort ascending
   for (int i = 0; i < n - 1; ++i) {

@@ -83,11 +83,23 @@ def test_config2_bqp60_optimum_and_kkt():
     d = np.load(os.path.join(GOLDEN, "bqp_60_1.npz"))
     At, b, c, K = g.bqpmom(60, d["Q"], d["e"])
     assert (int(K["s"]), At.shape[1]) == (1831, 1155281) == (gold["n"], gold["m"])
-    c = c / np.abs(c).max()
+    cmax = np.abs(c).max()
+    c = c / cmax
     X, obj, data = ManiSDP_unitdiag(At, _dense_b(b), c, K, dict(verbose=False, tol=1e-8))
     assert data["status"] == 0
     assert max(data["gap"], data["pinf"], data["dinf"]) <= 1e-8
     assert abs(obj - gold["obj_scaled"]) <= 1e-6 * abs(gold["obj_scaled"]), (obj, gold["obj_scaled"])
+    # oracle-free certificate: the relaxation is tight on this instance -- X is rank 1, its first row holds the moments
+    # (1, x_1..x_60, x_i x_j) of a +-1 vector x (bqpmom.m:8-14 basis order), and the BQP objective at x equals the SDP
+    # optimum; together with dinf = 0 (dual feasibility) weak duality makes x the exact minimiser over {-1,+1}^60
+    ev = np.linalg.eigvalsh(X)
+    assert ev[-2] <= 1e-6 * ev[-1]
+    x = X[0, 1:61] / X[0, 0]
+    assert np.max(np.abs(np.abs(x) - 1.0)) < 1e-5
+    xs = np.sign(x)
+    bqp_val = float(xs @ d["Q"] @ xs + d["e"] @ xs)
+    assert abs(bqp_val - obj * cmax) <= 1e-6 * abs(bqp_val), (bqp_val, obj * cmax)
+    assert abs(bqp_val - gold["obj"]) <= 1e-6 * abs(gold["obj"])
 
 
 # ---- config 3: quartic on the sphere q = 60 ----------------------------------------------------------------------------

@@ -1,3 +1,13 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 8 --steps 10 --warmup 3 --no-alt > gpurun_out/r2_bench_n8_b.json 2> gpurun_out/r2_bench_n8_b.err; python -c "import sys,json; d=json.loads([l for l in open('gpurun_out/r2_bench_n8_b.json') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], d['parity_check'], d['e2e']['value'], d['roofline']['ms_per_launch'])"; tail -2 gpurun_out/r2_bench_n8_b.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29546 tools/run_configs.py er:1000000 --verbose --opts='{"p0": 256, "delta": 24}' > gpurun_out/r2_c5_er1e6_p256_n8.log 2>&1; grep -v "OMP_NUM\|\*\*\*\*" gpurun_out/r2_c5_er1e6_p256_n8.log | tail -8 | cut -c1-1200
+timeout 600 python tools/run_configs.py bqp60 g1 bqp20 theta98 theta102 > gpurun_out/r2_configs_adaptive.jsonl 2>&1; cut -c1-900 gpurun_out/r2_configs_adaptive.jsonl
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 60 --csv --log-file gpurun_out/r2_theta_launches.csv python tools/theta_hv_bench.py 11 2 20 20 > /dev/null 2>&1; python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/r2_theta_launches.csv')) if len(r)>5]
+hdr=rows[0]; ik=hdr.index('Kernel Name'); iv=hdr.index('Metric Value')
+from collections import OrderedDict
+agg=OrderedDict()
+for r in rows[1:]:
+    k=r[ik][:70]; agg.setdefault(k,[]).append(float(r[iv].replace(',','')))
+for k,v in agg.items(): print(len(v), round(sum(v)/len(v)/1000,2),'us', k)
+PY
+timeout 900 python -m pytest tests -m gpu -q -x -k "full_solve or config4 or config3 or kkt or known_answer or sdplib or sharded or column" > gpurun_out/r2_pytest_e.log 2>&1; tail -5 gpurun_out/r2_pytest_e.log
