@@ -401,6 +401,9 @@ def run_ours(args, rank, world):
     if world == 1 and not args.no_cpu:
         chv, ct = cpu_sample(C, n, p, args.cpu_inner, repeats=args.cpu_steps, Y0=Y_timed_start)
         cpu = {"value": chv / ct, "unit": UNIT, "cores": _cpu_threads(), "host_cores": os.cpu_count(), "kind": "port",
+               "caveat": "the port's sparse*dense products use all host threads, its vector operations are single-threaded "
+                         "NumPy; MATLAB would thread those too, so a GPU/CPU ratio taken against this line overstates the "
+                         "gap to the real reference (a reported baseline, not a target)",
                "sample": f"oracle port replaying the first {args.cpu_steps} timed steps trustregions(maxiter=1, "
                          f"maxinner={args.cpu_inner}) of the same instance from the point where the GPU arm's timed "
                          f"region starts ({chv} Hv + {2 * args.cpu_steps} cost/gradient "

@@ -39,6 +39,58 @@ static int mgrid(const manisdp_handle* h, int64_t total, int per_block = MSDP_TH
 // ======================================================================================================================
 
 // K2 (sparse A): w_k = sum_e a_e <P_{i_e}, Q_{j_e}> ; mode 1 additionally r_k = w_k - b_k - y_k/sigma and sum r_k^2
+// The entries of a constraint are taken four at a time: indices first, then the eight operand rows, then the products --
+// the gathers of a batch are independent and in flight together (summation order unchanged).
+template <int GS, int VPL>
+__device__ __forceinline__ double sddmm_range(const int* __restrict__ ei, const int* __restrict__ ej,
+                                              const double* __restrict__ ea, const double* __restrict__ P,
+                                              const double* __restrict__ Q, int ld, int e0, int e1, int gl) {
+  const int nvec = ld / 2;
+  double acc = 0.0;
+  int e = e0;
+  for (; e + 4 <= e1; e += 4) {
+    double d[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* pi[4];
+    const double* qj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pi[u] = P + (size_t)ei[e + u] * ld;
+      qj[u] = Q + (size_t)ej[e + u] * ld;
+    }
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int c = gl + GS * t;
+      if (c < nvec) {
+        double2 a[4], bq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[u] = ldg2(pi[u] + 2 * c);
+          bq[u] = ldg2(qj[u] + 2 * c);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] += a[u].x * bq[u].x + a[u].y * bq[u].y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc = fma(ea[e + u], d[u], acc);
+  }
+  for (; e < e1; ++e) {
+    const double* p1 = P + (size_t)ei[e] * ld;
+    const double* q1 = Q + (size_t)ej[e] * ld;
+    double d = 0.0;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int c = gl + GS * t;
+      if (c < nvec) {
+        const double2 a = ldg2(p1 + 2 * c), bq = ldg2(q1 + 2 * c);
+        d += a.x * bq.x + a.y * bq.y;
+      }
+    }
+    acc = fma(ea[e], d, acc);
+  }
+  return acc;
+}
+
 template <int GS, int VPL>
 __global__ void __launch_bounds__(MSDP_THREADS)
     k_sddmm(const int* __restrict__ kptr, const int* __restrict__ ei, const int* __restrict__ ej,
@@ -48,26 +100,11 @@ __global__ void __launch_bounds__(MSDP_THREADS)
   __shared__ double sm[32];
   if (skip_if_stopped && st->stop != 0) return;
   const unsigned mask = group_mask<GS>();
-  const int gl = threadIdx.x % GS, nvec = ld / 2;
+  const int gl = threadIdx.x % GS;
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
   double q[1] = {0.0};
   for (int64_t k = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; k < m; k += ngroups) {
-    const int e0 = kptr[k], e1 = kptr[k + 1];
-    double acc = 0.0;
-    for (int e = e0; e < e1; ++e) {
-      const double* pi = P + (size_t)ei[e] * ld;
-      const double* qj = Q + (size_t)ej[e] * ld;
-      double d = 0.0;
-#pragma unroll
-      for (int t = 0; t < VPL; ++t) {
-        const int c = gl + GS * t;
-        if (c < nvec) {
-          const double2 a = ldg2(pi + 2 * c), bq = ldg2(qj + 2 * c);
-          d += a.x * bq.x + a.y * bq.y;
-        }
-      }
-      acc = fma(ea[e], d, acc);
-    }
+    double acc = sddmm_range<GS, VPL>(ei, ej, ea, P, Q, ld, kptr[k], kptr[k + 1], gl);
     acc = group_sum<GS>(acc, mask);
     if (mode == 1) acc = acc - b[k] - y[k] * inv_sigma;
     if (gl == 0) {
@@ -78,6 +115,48 @@ __global__ void __launch_bounds__(MSDP_THREADS)
   if (mode == 1) {
     double tot[1];
     __syncwarp();
+    if (grid_sum_last<1>(q, partials, &st->ticket, sm, tot)) {
+      if (threadIdx.x == 0) st->tmp[T_RR] = tot[0];
+    }
+  }
+}
+
+// segmented form (some constraint is long): one row group per SEGMENT of at most SDDMM_SEG entries ...
+template <int GS, int VPL>
+__global__ void __launch_bounds__(MSDP_THREADS)
+    k_sddmm_seg(const int* __restrict__ sptr, const int* __restrict__ ei, const int* __restrict__ ej,
+                const double* __restrict__ ea, const double* __restrict__ P, const double* __restrict__ Q, int ld,
+                int64_t nseg, double* __restrict__ segval, RtrState* st, int skip_if_stopped) {
+  if (skip_if_stopped && st->stop != 0) return;
+  const unsigned mask = group_mask<GS>();
+  const int gl = threadIdx.x % GS;
+  const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
+  for (int64_t sg = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; sg < nseg; sg += ngroups) {
+    double acc = sddmm_range<GS, VPL>(ei, ej, ea, P, Q, ld, sptr[sg], sptr[sg + 1], gl);
+    acc = group_sum<GS>(acc, mask);
+    if (gl == 0) segval[sg] = acc;
+  }
+}
+// ... and the per-constraint sums of the segment values in segment order (deterministic), with the mode-1 residual
+__global__ void __launch_bounds__(MSDP_THREADS)
+    k_sddmm_finish(const int* __restrict__ ksegs, const double* __restrict__ segval, int64_t m, double* __restrict__ out,
+                   int mode, const double* __restrict__ b, const double* __restrict__ y, double inv_sigma, RtrState* st,
+                   double* partials, int skip_if_stopped) {
+  __shared__ double sm[32];
+  if (skip_if_stopped && st->stop != 0) return;
+  double q[1] = {0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+    double acc = 0.0;
+    for (int sg = ksegs[k]; sg < ksegs[k + 1]; ++sg) acc += segval[sg];
+    if (mode == 1) {
+      acc = acc - b[k] - y[k] * inv_sigma;
+      q[0] += acc * acc;
+    }
+    out[k] = acc;
+  }
+  if (mode == 1) {
+    double tot[1];
     if (grid_sum_last<1>(q, partials, &st->ticket, sm, tot)) {
       if (threadIdx.x == 0) st->tmp[T_RR] = tot[0];
     }
@@ -519,6 +598,25 @@ int msdp_affine_setup(manisdp_handle* h, const manisdp_problem* pb) {
     ASparse& S = h->As;
     S.nnz = (int64_t)nnzA;
     MSDP_TRY(to_dev(h, &S.kptr, kptr));
+    {  // segments of at most SDDMM_SEG entries, built only when some constraint is longer than 2 segments
+      int maxlen = 0;
+      for (int64_t k = 0; k < m; ++k) maxlen = std::max(maxlen, kptr[(size_t)k + 1] - kptr[(size_t)k]);
+      if (maxlen > 2 * SDDMM_SEG) {
+        std::vector<int> sptr, ksegs((size_t)m + 1, 0);
+        for (int64_t k = 0; k < m; ++k) {
+          ksegs[(size_t)k] = (int)sptr.size();
+          for (int e = kptr[(size_t)k]; e < kptr[(size_t)k + 1]; e += SDDMM_SEG) sptr.push_back(e);
+        }
+        ksegs[(size_t)m] = (int)sptr.size();
+        S.nseg = (int64_t)sptr.size();
+        sptr.push_back(kptr[(size_t)m]);
+        // a segment ends where the next one starts, except at a constraint boundary: make that explicit
+        std::vector<int> send(sptr);
+        MSDP_TRY(to_dev(h, &S.sptr, send));
+        MSDP_TRY(to_dev(h, &S.ksegs, ksegs));
+        CUDA_TRY(h, cudaMalloc((void**)&S.segval, (size_t)std::max<int64_t>(1, S.nseg) * sizeof(double)));
+      }
+    }
     MSDP_TRY(to_dev(h, &S.ei, ei));
     MSDP_TRY(to_dev(h, &S.ej, ej));
     MSDP_TRY(to_dev(h, &S.ea, ea));
@@ -627,7 +725,7 @@ int msdp_affine_setup(manisdp_handle* h, const manisdp_problem* pb) {
 void msdp_affine_free(manisdp_handle* h) {
   void* ptrs[] = {h->Cdense, h->eS,     h->Mbuf,   h->Tbuf,   h->b,       h->y,       h->resid[0], h->resid[1],
                   h->wU,     h->wtmp,   h->As.kptr, h->As.ei, h->As.ej,   h->As.ea,   h->As.rptr,  h->As.rj,
-                  h->As.rk,  h->As.ra,  h->Ad.kptr, h->Ad.klin, h->Ad.ka, h->Ad.upos, h->Ad.lptr,  h->Ad.lk,
+                  h->As.rk,  h->As.ra,  h->As.sptr, h->As.ksegs, h->As.segval, h->Ad.kptr, h->Ad.klin, h->Ad.ka, h->Ad.upos, h->Ad.lptr,  h->Ad.lk,
                   h->Ad.la};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -648,11 +746,21 @@ static int apply_A(manisdp_handle* h, const double* P, const double* Q, double* 
                                                                 mode, h->b, h->y, inv_sigma, h->st, h->partials,
                                                                 skip_if_stopped);
   } else {
-    DISPATCH_GEOM(row_geom(h->ld), {
-      k_sddmm<GS, VPL><<<mgrid(h, h->m, MSDP_THREADS / GS), MSDP_THREADS, 0, h->stream>>>(
-          h->As.kptr, h->As.ei, h->As.ej, h->As.ea, P, Q, ld, h->m, out, mode, h->b, h->y, inv_sigma, h->st,
-          h->partials, skip_if_stopped);
-    });
+    if (h->As.nseg > 0) {  // some constraint is long (theta: the trace row): segments, then the per-constraint sums
+      DISPATCH_GEOM(row_geom(h->ld), {
+        k_sddmm_seg<GS, VPL><<<mgrid(h, h->As.nseg, MSDP_THREADS / GS), MSDP_THREADS, 0, h->stream>>>(
+            h->As.sptr, h->As.ei, h->As.ej, h->As.ea, P, Q, ld, h->As.nseg, h->As.segval, h->st, skip_if_stopped);
+      });
+      KERNEL_CHECK(h);
+      k_sddmm_finish<<<mgrid(h, h->m), MSDP_THREADS, 0, h->stream>>>(h->As.ksegs, h->As.segval, h->m, out, mode, h->b,
+                                                                   h->y, inv_sigma, h->st, h->partials, skip_if_stopped);
+    } else {
+      DISPATCH_GEOM(row_geom(h->ld), {
+        k_sddmm<GS, VPL><<<mgrid(h, h->m, MSDP_THREADS / GS), MSDP_THREADS, 0, h->stream>>>(
+            h->As.kptr, h->As.ei, h->As.ej, h->As.ea, P, Q, ld, h->m, out, mode, h->b, h->y, inv_sigma, h->st,
+            h->partials, skip_if_stopped);
+      });
+    }
   }
   KERNEL_CHECK(h);
   return MANISDP_OK;

@@ -54,7 +54,14 @@ struct ASparse {
   int *rptr = nullptr, *rj = nullptr, *rk = nullptr;
   double* ra = nullptr;
   int64_t nnz = 0;
+  // long constraints (e.g. the trace row of a theta SDP: n entries in ONE constraint) are cut into segments of at most
+  // SDDMM_SEG entries so that no row group walks thousands of dependent gathers alone: segment s covers the entries
+  // [sptr[s], sptr[s+1]) and constraint k owns the segments [ksegs[k], ksegs[k+1]).  nseg == 0: no constraint is long.
+  int *sptr = nullptr, *ksegs = nullptr;
+  double* segval = nullptr;
+  int64_t nseg = 0;
 };
+#define SDDMM_SEG 32
 
 // constraint pattern of At for the dense path: A as CSR over k with linear indices into the n x n matrix, and its
 // transpose as CSR over the linear index
