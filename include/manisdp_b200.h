@@ -238,6 +238,29 @@ int manisdp_get_stats(manisdp_t *h, manisdp_stats *out);
  * hess_bench, get_Y / set_Y / slot access (on the local n x pl slice) and get_stats are available. */
 int manisdp_col_split(manisdp_t *h);
 int manisdp_col_merge(manisdp_t *h);
+
+/* ---- single-process multi-GPU group (SURVEY 8b "Threading": one caller thread drives G devices) -----------------
+ * For host languages that call synchronously from ONE thread (MATLAB's MEX interface): the group owns one worker thread
+ * and one column-sharded ONLYUNITDIAG handle per device, creates the NCCL id in-process, and every group call runs the
+ * corresponding handle call on all devices and returns when all are done.  `prob` describes the WHOLE problem (kind
+ * ONLYUNITDIAG, full C; rank / world / device / row_* / nccl_unique_id / shard_layout are filled in by the group).
+ * Between calls the factor is merged (full width on every device); manisdp_group_tr_solve = split -> tr_solve -> merge.
+ * Results (Y, info, KKT record, rank) are those of device 0 -- identical on all devices by construction. */
+typedef struct manisdp_group manisdp_group_t;
+int manisdp_group_create(manisdp_group_t **out, const manisdp_problem *prob, int32_t ndev, const int32_t *devices);
+int manisdp_group_destroy(manisdp_group_t *g);
+int manisdp_group_size(const manisdp_group_t *g);
+const char *manisdp_group_last_error(const manisdp_group_t *g);
+int manisdp_group_set_Y(manisdp_group_t *g, const double *Y, int64_t p, int32_t layout);
+int manisdp_group_rand_Y(manisdp_group_t *g, int64_t p, uint64_t seed);
+int manisdp_group_get_Y(manisdp_group_t *g, double *Y, int32_t layout);
+int manisdp_group_get_stats(manisdp_group_t *g, manisdp_stats *out);
+int manisdp_group_cost(manisdp_group_t *g, double *f);
+int manisdp_group_tr_solve(manisdp_group_t *g, const manisdp_tr_options *opts, manisdp_tr_info *info);
+int manisdp_group_kkt(manisdp_group_t *g, int32_t delta, double eig_tol, int32_t update_dual, manisdp_kkt_info *out);
+int manisdp_group_rank_cut(manisdp_group_t *g, double theta, int32_t apply, int64_t *r, int64_t *p_new);
+int manisdp_group_escape(manisdp_group_t *g, int32_t nne, double alpha, int32_t line_search);
+int manisdp_group_line_search(manisdp_group_t *g, double *alpha);
 /* read-back of the integer index split r = j*n + i -> (i, j) of every stored entry of At, in CSC order, exactly as
  * the device kernels index with it (SURVEY 7 "index exactness"; BASELINE north_star: "A(YY') index handling must be
  * bit-exact").  *count = nnz(At); at most `cap` pairs are written; i / j may be NULL to query the count. */

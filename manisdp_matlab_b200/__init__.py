@@ -4,6 +4,6 @@ Public surface = the reference's four primal drivers with unchanged signatures (
 include/manisdp_b200.h (libmanisdp_b200.so, built from csrc/ by build.py).
 """
 from .solvers import ManiSDP, ManiSDP_onlyunitdiag, ManiSDP_unitdiag, ManiSDP_unittrace  # noqa: F401
-from ._lib import Handle, EngineError, load, LIB_PATH  # noqa: F401
+from ._lib import Handle, GroupHandle, EngineError, load, LIB_PATH  # noqa: F401
 
 __all__ = ["ManiSDP", "ManiSDP_onlyunitdiag", "ManiSDP_unitdiag", "ManiSDP_unittrace", "Handle", "EngineError", "load"]

@@ -100,6 +100,20 @@ SIGNATURES = {
     "manisdp_test_sym_eig": (C.c_int, [_f64p, C.c_int32, _f64p, _f64p]),
     "manisdp_col_split": (C.c_int, [_H]),
     "manisdp_col_merge": (C.c_int, [_H]),
+    "manisdp_group_create": (C.c_int, [C.POINTER(_H), C.POINTER(Problem), C.c_int32, C.POINTER(C.c_int32)]),
+    "manisdp_group_destroy": (C.c_int, [_H]),
+    "manisdp_group_size": (C.c_int, [_H]),
+    "manisdp_group_last_error": (C.c_char_p, [_H]),
+    "manisdp_group_set_Y": (C.c_int, [_H, _f64p, C.c_int64, C.c_int32]),
+    "manisdp_group_rand_Y": (C.c_int, [_H, C.c_int64, C.c_uint64]),
+    "manisdp_group_get_Y": (C.c_int, [_H, _f64p, C.c_int32]),
+    "manisdp_group_get_stats": (C.c_int, [_H, C.POINTER(Stats)]),
+    "manisdp_group_cost": (C.c_int, [_H, _f64p]),
+    "manisdp_group_tr_solve": (C.c_int, [_H, C.POINTER(TrOptions), C.POINTER(TrInfo)]),
+    "manisdp_group_kkt": (C.c_int, [_H, C.c_int32, C.c_double, C.c_int32, C.POINTER(KktInfo)]),
+    "manisdp_group_rank_cut": (C.c_int, [_H, C.c_double, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "manisdp_group_escape": (C.c_int, [_H, C.c_int32, C.c_double, C.c_int32]),
+    "manisdp_group_line_search": (C.c_int, [_H, _f64p]),
     "manisdp_get_index_split": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,
                                           C.POINTER(C.c_int64)]),
 }
@@ -388,3 +402,105 @@ def nccl_unique_id() -> bytes:
     if rc != 0:
         raise EngineError(f"manisdp_nccl_unique_id failed ({rc})")
     return bytes(buf)
+
+
+class GroupHandle:
+    """Single-process multi-GPU ONLYUNITDIAG solve (manisdp_group_*, csrc/group.cu): one caller thread, one worker
+    thread + one column-sharded handle per device inside the library.  Same method names as Handle for what the
+    ManiSDP_onlyunitdiag driver needs; the factor is merged (full width) between calls."""
+
+    def __init__(self, n, C_csc, devices):
+        import scipy.sparse as sp
+
+        self.lib = load()
+        self._g = _H()
+        pb = Problem()
+        pb.kind = ONLYUNITDIAG
+        pb.n = n
+        Cm = sp.csc_matrix(C_csc)
+        Cm.sort_indices()
+        jc, ir, pr = _as_u64(Cm.indptr), _as_u64(Cm.indices), _as_f64(Cm.data)
+        pb.C_jc, pb.C_ir, pb.C_pr = _pu(jc), _pu(ir), _pf(pr)
+        dev = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        rc = self.lib.manisdp_group_create(C.byref(self._g), C.byref(pb), len(devices), dev)
+        if rc != 0:
+            msg = self.lib.manisdp_group_last_error(None)
+            raise EngineError(f"manisdp_group_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.n = self.n_local = n
+        self.devices = list(devices)
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self.lib.manisdp_group_last_error(self._g)
+            raise EngineError(f"group {what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._g:
+            self.lib.manisdp_group_destroy(self._g)
+            self._g = _H()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.manisdp_group_get_stats(self._g, C.byref(s)), "get_stats")
+        return s
+
+    @property
+    def p(self):
+        return int(self.stats().p)
+
+    def set_Y(self, Y):
+        Y = _as_f64(Y)
+        assert Y.ndim == 2 and Y.shape[0] == self.n
+        self._ck(self.lib.manisdp_group_set_Y(self._g, _pf(Y), Y.shape[1], LAYOUT_ROWS), "set_Y")
+
+    def get_Y(self):
+        out = np.empty((self.n, self.p))
+        self._ck(self.lib.manisdp_group_get_Y(self._g, _pf(out), LAYOUT_ROWS), "get_Y")
+        return out
+
+    def rand_Y(self, p, seed=0):
+        self._ck(self.lib.manisdp_group_rand_Y(self._g, p, seed), "rand_Y")
+
+    def cost(self):
+        f = C.c_double()
+        self._ck(self.lib.manisdp_group_cost(self._g, C.cast(C.byref(f), _f64p)), "cost")
+        return f.value
+
+    def tr_solve(self, maxiter=0, maxinner=0, tolgradnorm=0.0, use_graph=1, **kw):
+        o = TrOptions()
+        o.maxiter, o.maxinner, o.tolgradnorm, o.use_graph = int(maxiter), int(maxinner), float(tolgradnorm), int(use_graph)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        info = TrInfo()
+        self._ck(self.lib.manisdp_group_tr_solve(self._g, C.byref(o), C.byref(info)), "tr_solve")
+        return info
+
+    def kkt(self, delta=8, eig_tol=0.0, update_dual=0):
+        k = KktInfo()
+        self._ck(self.lib.manisdp_group_kkt(self._g, delta, eig_tol, update_dual, C.byref(k)), "kkt")
+        return k
+
+    def rank_cut(self, theta, apply=True):
+        r, pn = C.c_int64(), C.c_int64()
+        self._ck(self.lib.manisdp_group_rank_cut(self._g, theta, int(apply), C.byref(r), C.byref(pn)), "rank_cut")
+        return r.value, pn.value
+
+    def escape(self, nne, alpha, line_search=0):
+        self._ck(self.lib.manisdp_group_escape(self._g, nne, alpha, line_search), "escape")
+
+    def line_search(self):
+        a = C.c_double()
+        self._ck(self.lib.manisdp_group_line_search(self._g, C.cast(C.byref(a), _f64p)), "line_search")
+        return a.value

@@ -24,6 +24,7 @@
 #include <nccl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 #include "dist.h"
 #include "kernels.cuh"
@@ -42,7 +43,9 @@ struct ColNccl {
   bool ok = false;
 } g_cn;
 
+std::mutex g_cn_mu;  // (the workers of a single-process group create their handles concurrently)
 bool col_nccl_load(std::string& why) {
+  std::lock_guard<std::mutex> lk(g_cn_mu);
   if (g_cn.ok) return true;
   for (const char* nm : {"libnccl.so.2", "libnccl.so"}) {
     g_cn.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);

@@ -79,9 +79,17 @@ def ManiSDP_onlyunitdiag(C, options=None):
     # Multi-GPU (extension): options.world > 1 with options.rank / options.nccl_id runs the same loop on a
     # column-sharded handle -- the trust-region solve on p/world columns per GPU, the outer-loop steps (eigen step, rank
     # step, escape) redundantly and identically on every rank on the merged factor.  One process per GPU calls this.
+    # options.devices = [d0, d1, ...] instead: ONE process drives all the listed GPUs (manisdp_group_*, csrc/group.cu) --
+    # the mode the MATLAB gateway uses; the group splits / merges inside its tr_solve.
     world = int(o.get("world", 1))
-    with _lib.Handle("onlyunitdiag", n, C_csc=C, device=o["device"], rank=int(o.get("rank", 0)), world=world,
-                     nccl_id=o.get("nccl_id"), layout="cols" if world > 1 else "rows") as h:
+    devices = o.get("devices")
+    if devices is not None and len(devices) > 0:
+        world = 1
+        opener = _lib.GroupHandle(n, C, list(devices))
+    else:
+        opener = _lib.Handle("onlyunitdiag", n, C_csc=C, device=o["device"], rank=int(o.get("rank", 0)), world=world,
+                             nccl_id=o.get("nccl_id"), layout="cols" if world > 1 else "rows")
+    with opener as h:
         _init_point(h, o)
         data["setup_seconds"] = time.perf_counter() - t0
         staged = False
@@ -127,6 +135,7 @@ def ManiSDP_onlyunitdiag(C, options=None):
         Y = h.get_Y()
         st = h.stats()
         data["launches"] = st.launches_total
+        data["n_devices"] = len(devices) if devices else world
     z = None
     X = S = None
     if n <= DENSE_OUTPUT_MAX_N:

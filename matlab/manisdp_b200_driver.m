@@ -21,7 +21,12 @@ if ~isfield(options, 'use_graph'); options.use_graph = 1; end
 fprintf('ManiSDP is starting...\n');
 if kind == 0
     n = size(C, 1); m = n;
-    h = manisdp_mex('create', 0, n, sparse(C));
+    if isfield(options, 'devices') && numel(options.devices) > 0
+        % several GPUs from this one MATLAB session: a multi-GPU group (column-sharded trust-region solve)
+        h = manisdp_mex('create', 0, n, sparse(C), double(options.devices(:)'));
+    else
+        h = manisdp_mex('create', 0, n, sparse(C));
+    end
 else
     n = K.s; m = length(b);
     h = manisdp_mex('create', kind, n, sparse(At), b, c);

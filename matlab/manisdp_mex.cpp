@@ -9,6 +9,12 @@
  *
  * Usage from MATLAB (see ManiSDP_onlyunitdiag.m etc. in this directory):
  *   h    = manisdp_mex('create', kind, n, C)                      kind 0: C sparse n x n
+ *   h    = manisdp_mex('create', 0, n, C, devices)                several GPUs from this one MATLAB session: devices =
+ *                                                                 [0 1 ... ] (0-based CUDA ordinals) creates a group
+ *                                                                 (manisdp_group_*: one worker thread + one column-sharded
+ *                                                                 handle per device inside the library); set_Y, get_Y,
+ *                                                                 rand_Y, cost, tr_solve, kkt, rank_cut, escape,
+ *                                                                 line_search, stats, destroy work on it unchanged
  *   h    = manisdp_mex('create', kind, n, At, b, c)               kind 1..3: SeDuMi data
  *          manisdp_mex('set_Y', h, Y, layout)                     layout 0: p x n (unit-diag drivers), 1: n x p
  *   Y    = manisdp_mex('get_Y', h, layout)
@@ -35,11 +41,15 @@
 #include "mex.h"
 
 static std::vector<manisdp_t*> g_handles;
+static std::vector<manisdp_group_t*> g_groups;  // same index space as g_handles: exactly one of the two is non-null
 
 static void at_exit() {
   for (manisdp_t* h : g_handles)
     if (h) manisdp_destroy(h);
+  for (manisdp_group_t* g : g_groups)
+    if (g) manisdp_group_destroy(g);
   g_handles.clear();
+  g_groups.clear();
 }
 
 static void fail(manisdp_t* h, int rc, const char* what) {
@@ -54,12 +64,28 @@ static void fail(manisdp_t* h, int rc, const char* what) {
     if (_rc != 0) fail(h, _rc, what); \
   } while (0)
 
-static manisdp_t* handle_of(const mxArray* a) {
+static uint64_t index_of(const mxArray* a) {
   if (!mxIsUint64(a) || mxGetNumberOfElements(a) != 1) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "bad handle");
   const uint64_t idx = *(const uint64_t*)mxGetData(a);
-  if (idx >= g_handles.size() || !g_handles[idx]) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "stale handle");
-  return g_handles[idx];
+  if (idx >= g_handles.size() || (!g_handles[idx] && !g_groups[idx])) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "stale handle");
+  return idx;
 }
+
+static void gfail(manisdp_group_t* g, int rc, const char* what) {
+  const char* msg = manisdp_group_last_error(g);
+  char id[64];
+  snprintf(id, sizeof(id), "ManiSDP:b200:E%d", -rc);
+  mexErrMsgIdAndTxt(id, "%s failed (%d): %s", what, rc, msg ? msg : "");
+}
+#define GCK(g, expr, what)            \
+  do {                                \
+    int _rc = (expr);                 \
+    if (_rc != 0) gfail(g, _rc, what); \
+  } while (0)
+
+// commands on a multi-GPU group (created with a device list); the outputs have the same shapes as on a single handle
+static void group_command(manisdp_group_t* g, const std::string& c, const char* cmd, uint64_t idx, int nlhs, mxArray* plhs[],
+                          int nrhs, const mxArray* prhs[]);
 
 static double field_or(const mxArray* s, const char* name, double dflt) {
   const mxArray* f = mxIsStruct(s) ? mxGetField(s, 0, name) : nullptr;
@@ -118,25 +144,41 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       }
     }
     manisdp_t* h = nullptr;
-    int rc = manisdp_create(&h, &pb);
-    if (rc != 0) fail(nullptr, rc, "manisdp_create");
+    manisdp_group_t* grp = nullptr;
+    if (pb.kind == MANISDP_ONLYUNITDIAG && nrhs > 4 && mxGetNumberOfElements(prhs[4]) > 0) {
+      // device list: one MATLAB session drives several GPUs (SURVEY 8b "Threading")
+      const size_t nd = mxGetNumberOfElements(prhs[4]);
+      std::vector<int32_t> dev(nd);
+      for (size_t i = 0; i < nd; ++i) dev[i] = (int32_t)mxGetPr(prhs[4])[i];
+      int rc = manisdp_group_create(&grp, &pb, (int32_t)nd, dev.data());
+      if (rc != 0) gfail(nullptr, rc, "manisdp_group_create");
+    } else {
+      int rc = manisdp_create(&h, &pb);
+      if (rc != 0) fail(nullptr, rc, "manisdp_create");
+    }
     if (g_handles.empty()) {
       mexLock();
       mexAtExit(at_exit);
     }
     g_handles.push_back(h);
+    g_groups.push_back(grp);
     plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
     *(uint64_t*)mxGetData(plhs[0]) = (uint64_t)(g_handles.size() - 1);
     return;
   }
 
-  manisdp_t* h = handle_of(prhs[1]);
+  if (nrhs < 2) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "missing handle");
+  const uint64_t hidx = index_of(prhs[1]);
+  if (g_groups[hidx]) {
+    group_command(g_groups[hidx], c, cmd, hidx, nlhs, plhs, nrhs, prhs);
+    return;
+  }
+  manisdp_t* h = g_handles[hidx];
   manisdp_stats st;
 
   if (c == "destroy") {
-    const uint64_t idx = *(const uint64_t*)mxGetData(prhs[1]);
     manisdp_destroy(h);
-    g_handles[idx] = nullptr;
+    g_handles[hidx] = nullptr;
   } else if (c == "set_Y") {
     const int layout = (int)mxGetScalar(prhs[3]);
     const int64_t p = layout == MANISDP_LAYOUT_ROWS ? (int64_t)mxGetM(prhs[2]) : (int64_t)mxGetN(prhs[2]);
@@ -232,5 +274,77 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     plhs[0] = scalar_struct(names, vals, 11);
   } else {
     mexErrMsgIdAndTxt("ManiSDP:b200:arg", "unknown command '%s'", cmd);
+  }
+}
+
+static void group_command(manisdp_group_t* g, const std::string& c, const char* cmd, uint64_t idx, int nlhs, mxArray* plhs[],
+                          int nrhs, const mxArray* prhs[]) {
+  manisdp_stats st;
+  if (c == "destroy") {
+    manisdp_group_destroy(g);
+    g_groups[idx] = nullptr;
+  } else if (c == "set_Y") {
+    const int layout = (int)mxGetScalar(prhs[3]);
+    const int64_t p = layout == MANISDP_LAYOUT_ROWS ? (int64_t)mxGetM(prhs[2]) : (int64_t)mxGetN(prhs[2]);
+    GCK(g, manisdp_group_set_Y(g, mxGetPr(prhs[2]), p, layout), "set_Y");
+  } else if (c == "get_Y") {
+    const int layout = (int)mxGetScalar(prhs[2]);
+    GCK(g, manisdp_group_get_stats(g, &st), "get_stats");
+    plhs[0] = layout == MANISDP_LAYOUT_ROWS ? mxCreateDoubleMatrix((mwSize)st.p, (mwSize)st.n, mxREAL)
+                                            : mxCreateDoubleMatrix((mwSize)st.n, (mwSize)st.p, mxREAL);
+    GCK(g, manisdp_group_get_Y(g, mxGetPr(plhs[0]), layout), "get_Y");
+  } else if (c == "rand_Y") {
+    GCK(g, manisdp_group_rand_Y(g, (int64_t)mxGetScalar(prhs[2]), (uint64_t)mxGetScalar(prhs[3])), "rand_Y");
+  } else if (c == "cost") {
+    double f = 0;
+    GCK(g, manisdp_group_cost(g, &f), "cost");
+    plhs[0] = mxCreateDoubleScalar(f);
+  } else if (c == "tr_solve") {
+    manisdp_tr_options o;
+    memset(&o, 0, sizeof(o));
+    const mxArray* s = nrhs > 2 ? prhs[2] : nullptr;
+    if (s) {
+      o.maxiter = (int32_t)field_or(s, "maxiter", 0);
+      o.maxinner = (int32_t)field_or(s, "maxinner", 0);
+      o.tolgradnorm = field_or(s, "tolgradnorm", 0);
+      o.use_graph = (int32_t)field_or(s, "use_graph", 1);
+    }
+    manisdp_tr_info info;
+    GCK(g, manisdp_group_tr_solve(g, &o, &info), "tr_solve");
+    const char* names[] = {"cost", "gradnorm", "Delta", "seconds", "hv_count", "iters", "accepted", "stop_reason"};
+    const double vals[] = {info.cost, info.gradnorm, info.Delta, info.seconds, (double)info.hv_count,
+                           (double)info.iters, (double)info.accepted, (double)info.stop_reason};
+    plhs[0] = scalar_struct(names, vals, 8);
+  } else if (c == "kkt") {
+    manisdp_kkt_info k;
+    GCK(g, manisdp_group_kkt(g, (int32_t)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), (int32_t)mxGetScalar(prhs[4]), &k),
+        "kkt");
+    const char* names[] = {"obj", "by", "pinf", "dinf", "gap", "lam_min", "lam_max", "z_sum", "nneg", "eig_iters",
+                           "eig_resid", "eig_converged"};
+    const double vals[] = {k.obj, k.by, k.pinf, k.dinf, k.gap, k.lam_min, k.lam_max, k.z_sum, (double)k.nneg,
+                           (double)k.eig_iters, k.eig_resid, (double)k.eig_converged};
+    plhs[0] = scalar_struct(names, vals, 12);
+  } else if (c == "rank_cut") {
+    int64_t r = 0, p = 0;
+    GCK(g, manisdp_group_rank_cut(g, mxGetScalar(prhs[2]), (int32_t)mxGetScalar(prhs[3]), &r, &p), "rank_cut");
+    plhs[0] = mxCreateDoubleScalar((double)r);
+    if (nlhs > 1) plhs[1] = mxCreateDoubleScalar((double)p);
+  } else if (c == "escape") {
+    GCK(g, manisdp_group_escape(g, (int32_t)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), (int32_t)mxGetScalar(prhs[4])),
+        "escape");
+  } else if (c == "line_search") {
+    double a = 0;
+    GCK(g, manisdp_group_line_search(g, &a), "line_search");
+    plhs[0] = mxCreateDoubleScalar(a);
+  } else if (c == "stats") {
+    GCK(g, manisdp_group_get_stats(g, &st), "get_stats");
+    const char* names[] = {"n", "m", "p", "nnzC", "nnzA", "s_mode", "a_mode", "hv_total", "launches_total",
+                           "bytes_per_hv", "flops_per_hv", "n_devices"};
+    const double vals[] = {(double)st.n, (double)st.m, (double)st.p, (double)st.nnzC, (double)st.nnzA,
+                           (double)st.s_mode, (double)st.a_mode, (double)st.hv_total, (double)st.launches_total,
+                           st.bytes_per_hv, st.flops_per_hv, (double)manisdp_group_size(g)};
+    plhs[0] = scalar_struct(names, vals, 12);
+  } else {
+    mexErrMsgIdAndTxt("ManiSDP:b200:arg", "command '%s' is not available on a multi-GPU group", cmd);
   }
 }
