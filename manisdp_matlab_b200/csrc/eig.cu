@@ -18,6 +18,15 @@
 // coarse accounting of the eigen step (MANISDP_EIG_DEBUG=1 prints it at destroy): device wait vs host Rayleigh-Ritz
 static double g_eig_wait_s = 0.0, g_eig_host_s = 0.0;
 static long g_eig_iters_total = 0;
+// rank step (MANISDP_EIG_DEBUG): Gram kernel + copy, host eigenvalues, host eigenvectors, installing the cut factor
+static double g_rank_gram_s = 0.0, g_rank_vals_s = 0.0, g_rank_vecs_s = 0.0, g_rank_install_s = 0.0;
+static long g_rank_calls = 0;
+struct ScopedSeconds {
+  double& acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit ScopedSeconds(double& a) : acc(a) {}
+  ~ScopedSeconds() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 #define EIG_TR 32       // rows per shared-memory tile
 #define EIG_MAXNB 48    // 3 * block size
@@ -619,6 +628,9 @@ void msdp_eig_release(manisdp_handle* h) {
   if (getenv("MANISDP_EIG_DEBUG") && g_eig_iters_total > 0)
     fprintf(stderr, "[manisdp eig] iterations %ld, device wait %.3f s, host part (RR + launches) %.3f s\n",
             g_eig_iters_total, g_eig_wait_s, g_eig_host_s);
+  if (getenv("MANISDP_EIG_DEBUG") && g_rank_calls > 0)
+    fprintf(stderr, "[manisdp rank] %ld decompositions: gram+copy %.3f s, eigenvalues (incl. gram) %.3f s, eigenvectors %.3f s, "
+                    "install %.3f s\n", g_rank_calls, g_rank_gram_s, g_rank_vals_s, g_rank_vecs_s, g_rank_install_s);
   auto it = g_store.find(h);
   if (it != g_store.end()) {
     eig_free(it->second.lo);
@@ -808,7 +820,12 @@ int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, in
   g_store_mu.unlock();
   if (es.rank_version != h->y_version || es.rank_p != p) {
     std::vector<double>& G = es.rank_G;
-    MSDP_TRY(gram_general(h, h->Ybuf[h->pt], (int)h->ld, p, h->Ybuf[h->pt], (int)h->ld, p, G));
+    g_rank_calls++;
+    {
+      ScopedSeconds t(g_rank_gram_s);
+      MSDP_TRY(gram_general(h, h->Ybuf[h->pt], (int)h->ld, p, h->Ybuf[h->pt], (int)h->ld, p, G));
+    }
+    ScopedSeconds tv(g_rank_vals_s);
     for (int i = 0; i < p; ++i)
       for (int j = i + 1; j < p; ++j) {
         const double v = 0.5 * (G[(size_t)i * p + j] + G[(size_t)j * p + i]);
@@ -830,6 +847,7 @@ int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, in
       if (sqrt(std::max(0.0, ev[i])) >= theta * s1t) ++rt;
     if (apply && rt <= p - 1 && rt >= 1 && !es.rank_have_Z) {
       std::vector<double> ev2;
+      ScopedSeconds tz(g_rank_vecs_s);
       if (!sym_eig(es.rank_G, p, ev2, es.rank_Z, true))
         return msdp_fail(h, MANISDP_E_NUMERIC, "rank_cut: eigen-decomposition failed");
       es.rank_ev = ev2;
@@ -844,6 +862,7 @@ int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, in
     if (sqrt(std::max(0.0, ev[i])) >= theta * s1) ++r;
   if (r_out) *r_out = r;
   if (apply && r <= p - 1 && r >= 1) {
+    ScopedSeconds ti(g_rank_install_s);
     // Y <- Y * U_r  (= V(:,1:r)'.*e(1:r) of the reference's p x n layout, :93-96)
     std::vector<double> Cm((size_t)p * r);
     for (int q = 0; q < p; ++q)
