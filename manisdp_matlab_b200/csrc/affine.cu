@@ -650,11 +650,16 @@ int msdp_affine_setup(manisdp_handle* h, const manisdp_problem* pb) {
     }
     // transpose over the touched positions (stable: k ascending inside a position)
     std::vector<int> order((size_t)nnzA);
-    std::iota(order.begin(), order.end(), 0);
     std::vector<int> kof((size_t)nnzA);
     for (int64_t k = 0; k < m; ++k)
       for (int e = kptr[(size_t)k]; e < kptr[(size_t)k + 1]; ++e) kof[(size_t)e] = (int)k;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return klin[(size_t)a] < klin[(size_t)b]; });
+    {  // stable counting sort of the entries by linear position (positions < n*n: one pass instead of a comparison sort
+       // of 4.8 M entries on BQP-60)
+      std::vector<int> cnt((size_t)nn + 1, 0);
+      for (uint64_t e = 0; e < nnzA; ++e) cnt[(size_t)klin[(size_t)e] + 1]++;
+      for (uint64_t q = 0; q < nn; ++q) cnt[(size_t)q + 1] += cnt[(size_t)q];
+      for (uint64_t e = 0; e < nnzA; ++e) order[(size_t)cnt[(size_t)klin[(size_t)e]]++] = (int)e;
+    }
     std::vector<int> upos, lptr, lk((size_t)nnzA);
     std::vector<double> la((size_t)nnzA);
     for (size_t q = 0; q < order.size(); ++q) {

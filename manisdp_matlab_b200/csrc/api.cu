@@ -75,6 +75,22 @@ static int grid_for(const manisdp_handle* h, int64_t total) {
 // ---- allocation ----------------------------------------------------------------------------------------------------
 static int64_t rows_alloc(const manisdp_handle* h) { return msdp_rows_per_rank(h->n, h->world); }
 
+int msdp_scratch(manisdp_handle* h, int slot, size_t bytes, void** out) {
+  if (bytes > h->scratch_cap[slot]) {
+    if (h->scratch[slot]) {
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      cudaFree(h->scratch[slot]);
+      h->scratch[slot] = nullptr;
+      h->scratch_cap[slot] = 0;
+    }
+    const size_t cap = bytes + bytes / 2 + 4096;
+    CUDA_TRY(h, cudaMalloc(&h->scratch[slot], cap));
+    h->scratch_cap[slot] = cap;
+  }
+  *out = h->scratch[slot];
+  return MANISDP_OK;
+}
+
 int msdp_resize(manisdp_handle* h, int64_t p) {
   if (p < 1) return msdp_fail(h, MANISDP_E_ARG, "p must be >= 1");
   const int64_t ld = 4 * ((p + 3) / 4);
@@ -428,6 +444,8 @@ static void free_all(manisdp_handle* h) {
   if (h->spmm_bptr) cudaFree(h->spmm_bptr);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->owner_bptr) cudaFree(h->owner_bptr);
+  for (void* q : h->scratch)
+    if (q) cudaFree(q);
   void* bm[] = {h->bm_col, h->bm_row, h->bm_chunk, h->bm_val, h->bm_part};
   for (void* q : bm)
     if (q) cudaFree(q);

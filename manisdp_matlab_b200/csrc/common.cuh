@@ -186,8 +186,13 @@ struct manisdp_handle {
   void* col_comm = nullptr;             // ncclComm_t
   double* col_rowvec = nullptr;         // n: per-row partial sums on their way through the all-reduce
   double* col_pack = nullptr;           // 8 + 2n: update packet [6 scalars, pad | rowsum(Y.*r') | rowsum(Y.*mdelta)]
+  // grow-only device scratch buffers of the outer-loop steps (Gram partials, combination staging): the rank step and the
+  // escape step run once per outer iteration and used to pay two to four cudaMalloc / cudaFree pairs each
+  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_cap[4] = {0, 0, 0, 0};
   std::string err;
 };
+int msdp_scratch(manisdp_handle* h, int slot, size_t bytes, void** out);  // api.cu
 
 // ---- tracing: one NVTX range per phase of the hot path (visible in Nsight Systems / ncu --nvtx; no cost when no
 // tool is attached: NVTX v3 is header-only and resolves its injection library lazily) -----------------------------

@@ -753,8 +753,9 @@ static int gram_general(manisdp_handle* h, const double* A, int lda, int ka, con
   int nchunks = (int)std::min<int64_t>(std::max<int64_t>(1, (32ll << 20) / (int64_t)(nent * 8)), 148);
   nchunks = (int)std::min<int64_t>(nchunks, std::max<int64_t>(1, h->nloc / EIG_TR));
   double *part = nullptr, *dev = nullptr;
-  CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)nchunks * nent * sizeof(double)));
-  cudaError_t e = cudaMalloc((void**)&dev, nent * sizeof(double));
+  MSDP_TRY(msdp_scratch(h, 0, (size_t)nchunks * nent * sizeof(double), (void**)&part));
+  MSDP_TRY(msdp_scratch(h, 1, nent * sizeof(double), (void**)&dev));
+  cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) {
     dim3 grid(ti, tj, nchunks);
     k_gram_general<<<grid, MSDP_THREADS, 0, h->stream>>>(A, lda, ka, B, ldb, kb, h->nloc, part);
@@ -768,8 +769,6 @@ static int gram_general(manisdp_handle* h, const double* A, int lda, int ka, con
   if (e == cudaSuccess && rc == MANISDP_OK)
     e = cudaMemcpyAsync(out.data(), dev, nent * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(part);
-  if (dev) cudaFree(dev);
   if (rc != MANISDP_OK) return rc;
   CUDA_TRY(h, e);
   return MANISDP_OK;
@@ -781,10 +780,16 @@ static int install_combination(manisdp_handle* h, const std::vector<double>& Cm,
   const int64_t ldn = 4 * ((pnew + 3) / 4);
   const int64_t rows = msdp_rows_per_rank(h->n, h->world);
   double *tmp = nullptr, *dC = nullptr, *dD = nullptr;
-  CUDA_TRY(h, cudaMalloc((void**)&tmp, (size_t)rows * ldn * sizeof(double)));
+  MSDP_TRY(msdp_scratch(h, 2, (size_t)rows * ldn * sizeof(double), (void**)&tmp));
   CUDA_TRY(h, cudaMemsetAsync(tmp, 0, (size_t)rows * ldn * sizeof(double), h->stream));
-  cudaError_t e = cudaMalloc((void**)&dC, std::max<size_t>(1, Cm.size()) * sizeof(double));
-  if (e == cudaSuccess && !Dm.empty()) e = cudaMalloc((void**)&dD, Dm.size() * sizeof(double));
+  {
+    const size_t nc = std::max<size_t>(1, Cm.size()), nd = Dm.size();
+    double* cd = nullptr;
+    MSDP_TRY(msdp_scratch(h, 3, (nc + nd + 2) * sizeof(double), (void**)&cd));
+    dC = cd;
+    if (nd) dD = cd + nc;
+  }
+  cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaMemcpyAsync(dC, Cm.data(), Cm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess && dD)
     e = cudaMemcpyAsync(dD, Dm.data(), Dm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
@@ -803,9 +808,6 @@ static int install_combination(manisdp_handle* h, const std::vector<double>& Cm,
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     }
   }
-  cudaFree(tmp);
-  if (dC) cudaFree(dC);
-  if (dD) cudaFree(dD);
   MSDP_TRY(rc);
   CUDA_TRY(h, e);
   return MANISDP_OK;

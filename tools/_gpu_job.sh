@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_sharded.py tests/test_mex_gateway.py -m gpu -q -x > gpurun_out/r2_pytest_g.log 2>&1; tail -15 gpurun_out/r2_pytest_g.log
+MANISDP_EIG_DEBUG=1 timeout 300 python tools/run_configs.py theta112 2>&1 | grep -v "^{" | tail -3
+MANISDP_EIG_DEBUG=1 timeout 300 python tools/run_configs.py bqp60 2>&1 | tail -3 | cut -c1-400
