@@ -49,7 +49,9 @@ enum {
   MANISDP_ONLYUNITDIAG = 0, /* src/primal/ManiSDP_onlyunitdiag.m : oblique rows, f = 1/2 <C, YY'> */
   MANISDP_UNITDIAG = 1,     /* src/primal/ManiSDP_unitdiag.m     : oblique rows + AL on A(X) = b   */
   MANISDP_UNITTRACE = 2,    /* src/primal/ManiSDP_unittrace.m    : unit Frobenius sphere + AL      */
-  MANISDP_GENERAL = 3       /* src/primal/ManiSDP.m              : Euclidean + AL                  */
+  MANISDP_GENERAL = 3,      /* src/primal/ManiSDP.m              : Euclidean + AL                  */
+  MANISDP_MULTIBLOCK = 4    /* src/primal/ManiSDP_multiblock.m   : product of oblique / Euclidean blocks + AL
+                               (manifold ops: src/basicfunction/multiblockmanifold.m:1-42, src/C-files/ sources) */
 };
 
 enum { MANISDP_LAYOUT_ROWS = 0, MANISDP_LAYOUT_COLS = 1 };
@@ -97,6 +99,12 @@ typedef struct {
    * manisdp_col_split and manisdp_col_merge, ceil(p/world) COLUMNS of the factor: the Hessian product needs no exchange
    * of the factor, only all-reduces of per-row scalars (n doubles) -- SURVEY 8e "p-sharding". */
   int32_t shard_layout;
+  /* MANISDP_MULTIBLOCK only (ManiSDP_multiblock.m:7-9): K.s = block_sizes[0..nblocks), the first `nob` blocks have a
+   * unit diagonal (K.nob).  n must equal sum(block_sizes); At has sum(block_sizes[i]^2) rows -- the stacked column-major
+   * vecs of the blocks, exactly the reference's x (:44, :67-72) -- and c that many entries.  The library maps row r to
+   * (block, i, j) in 64-bit integer arithmetic at create time. */
+  int32_t nblocks, nob;
+  const int64_t *block_sizes;
 } manisdp_problem;
 enum { MANISDP_SHARD_ROWS = 0, MANISDP_SHARD_COLS = 1 };
 
@@ -268,6 +276,36 @@ int manisdp_get_index_split(manisdp_t *h, int64_t *i, int64_t *j, int64_t cap, i
 /* host-only diagnostic (no GPU): eigen-decomposition of a small dense symmetric matrix A (n x n, row-major) with the
  * solver the eigen / rank steps use for their projected problems; w ascending, eigenvectors in the columns of V */
 int manisdp_test_sym_eig(const double *A, int32_t n, double *w, double *V);
+
+
+/* ---- multi-block handles (kind MANISDP_MULTIBLOCK; src/primal/ManiSDP_multiblock.m) ------------------------------
+ * The blocks live on the device as ONE factor of N = sum(n_i) rows: block i owns rows [off_i, off_i + n_i) and the
+ * leading p_i of the ld columns (the rest are zero and stay zero under every closure and manifold operation), so the
+ * product-manifold operations of src/C-files/ projc.cpp, retrc.cpp, innerc.cpp, lincombc.cpp are the fused row kernels of the
+ * single-block drivers with a per-row manifold switch, batched over all blocks in one launch.  cost / grad / hess /
+ * tr_solve / line_search / set_dual / set_sigma / slot access work as for the other affine kinds (slots are N x pmax).
+ * Host layout of a multi-block point ("cat"): the blocks one after the other, block i as n_i x p_i row-major -- the
+ * memory image of the reference's p_i x n_i column-major cell Y{i}. */
+int manisdp_mb_set_Y(manisdp_t *h, const double *Ycat, const int64_t *p);
+int manisdp_mb_get_Y(manisdp_t *h, double *Ycat);     /* sum(n_i * p_i) doubles */
+int manisdp_mb_get_widths(manisdp_t *h, int64_t *p);  /* nblocks entries */
+/* M.rand() of multiblockmanifold.m:32-35 (randc.cpp:52-80): N(0,1) entries, unit rows on the first nob blocks */
+int manisdp_mb_rand_Y(manisdp_t *h, const int64_t *p, uint64_t seed);
+/* KKT step of ManiSDP_multiblock.m:66-97: obj, pinf, y <- y - sigma*(A x - b), by (with the z of the unit-diagonal blocks),
+ * and eig(S{i}) of every block (batched, one eigen-decomposition per block); dinf = max_i dinfs[i].  dinfs / nneg
+ * (number of negative eigenvalues of each block, uncapped) may be NULL.  The eigenvectors stay on the device for
+ * manisdp_mb_update. */
+int manisdp_mb_kkt(manisdp_t *h, int32_t update_dual, manisdp_kkt_info *out, double *dinfs, int32_t *nneg);
+/* all eigenvalues of the dual slack of block `blk` from the last manisdp_mb_kkt (ascending, n_blk doubles) and,
+ * if vecs != NULL, the eigenvectors (n_blk x n_blk, column k = k-th eigenvector, row-major) */
+int manisdp_mb_get_block_eigs(manisdp_t *h, int32_t blk, double *vals, double *vecs);
+/* rank cut + escape of every block, ManiSDP_multiblock.m:114-153: blocks with n_i >= min_facsize get
+ * r_i = #{s >= theta*s_1} from the p_i x p_i Gram matrix (replaces svd(Y{i})), the rank-r_i truncation when r_i < p_i,
+ * and nne_i escape directions (the lowest eigenvectors of S{i} kept by manisdp_mb_kkt): appended scaled by alpha and
+ * (unit-diagonal blocks) renormalised when line_search = 0, staged in SLOT_U for manisdp_line_search when 1.
+ * p_new (nblocks, may be NULL) receives the new widths. */
+int manisdp_mb_update(manisdp_t *h, double theta, int32_t delta, double alpha, int32_t line_search,
+                      int32_t min_facsize, int64_t *p_new);
 
 #ifdef __cplusplus
 }

@@ -360,3 +360,70 @@ def theta_random(n: int, nedges_draw: int, seed: int):
     b[m] = 1.0
     c = -np.ones(n * n)
     return At, b, c, {"s": n}
+
+
+# --------------------------------------------------------------------------------------------
+# multi-block instances (inputs of ManiSDP_multiblock: K.s = block orders, K.nob = number of
+# leading unit-diagonal blocks; At has sum(n_i^2) rows, the stacked column-major vecs of the blocks)
+# --------------------------------------------------------------------------------------------
+def multiblock_random(nset, nob: int, m: int, seed: int, rank: int = 2):
+    """Random feasible, bounded multi-block SDP in the format ManiSDP_multiblock.m:7 takes.
+    Feasible point: X_i = V_i V_i' with `rank` columns (unit rows for the first nob blocks);
+    constraints: m sparse symmetric matrices, each supported on one or two blocks, b = A(X0);
+    objective: a positive definite matrix per block, so the problem is bounded below."""
+    rng = np.random.default_rng(seed)
+    nset = [int(v) for v in nset]
+    off = np.concatenate([[0], np.cumsum([v * v for v in nset])]).astype(np.int64)
+    x0 = []
+    for i, n in enumerate(nset):
+        V = rng.standard_normal((n, min(rank, n)))
+        if i < nob:
+            V /= np.linalg.norm(V, axis=1, keepdims=True)
+        x0.append((V @ V.T).reshape(-1, order="F"))
+    x0 = np.concatenate(x0)
+    rows, cols, vals = [], [], []
+    for k in range(m):
+        for blk in rng.choice(len(nset), size=min(len(nset), int(rng.integers(1, 3))), replace=False):
+            n = nset[blk]
+            for _ in range(int(rng.integers(1, 4))):
+                a, bb = int(rng.integers(0, n)), int(rng.integers(0, n))
+                v = float(rng.standard_normal())
+                if a == bb:
+                    if blk < nob:
+                        continue  # the diagonal of a unit-diagonal block is fixed by the manifold
+                    rows.append(off[blk] + a * n + a); cols.append(k); vals.append(v)
+                else:
+                    rows += [off[blk] + bb * n + a, off[blk] + a * n + bb]
+                    cols += [k, k]
+                    vals += [0.5 * v, 0.5 * v]
+    At = sp.csc_matrix((vals, (rows, cols)), shape=(int(off[-1]), m))
+    At.sum_duplicates()
+    b = At.T @ x0
+    c = []
+    for n in nset:
+        G = rng.standard_normal((n, n))
+        c.append((G @ G.T / n + 0.5 * np.eye(n)).reshape(-1, order="F"))
+    return At, b, np.concatenate(c), {"s": nset, "nob": int(nob)}
+
+
+def embed_multiblock(At, c, K):
+    """Block-diagonal embedding of a multi-block problem into ONE PSD cone of order N = sum(n_i):
+    returns (At_big (N*N, m), c_big (N*N,), N, row offsets).  The off-diagonal blocks of X carry no
+    cost and no constraint, and every principal block of a PSD matrix is PSD, so the optimum over
+    {X >= 0 of order N} equals the multi-block optimum when no block is unit-diagonal (K.nob = 0) --
+    an independent route to the optimum through the single-block drivers (test pin)."""
+    nset = [int(v) for v in np.atleast_1d(K["s"])]
+    N = int(sum(nset))
+    off2 = np.concatenate([[0], np.cumsum([v * v for v in nset])]).astype(np.int64)
+    roff = np.concatenate([[0], np.cumsum(nset)]).astype(np.int64)
+    mp = np.empty(int(off2[-1]), dtype=np.int64)
+    for i, n in enumerate(nset):
+        loc = np.arange(n * n, dtype=np.int64)
+        a, bb = loc % n, loc // n
+        mp[off2[i]:off2[i + 1]] = (roff[i] + bb) * N + (roff[i] + a)
+    At = sp.coo_matrix(At)
+    At_big = sp.csc_matrix((At.data, (mp[At.row], At.col)), shape=(N * N, At.shape[1]))
+    c = np.asarray(c, dtype=np.float64).ravel()
+    c_big = np.zeros(N * N)
+    c_big[mp] = c
+    return At_big, c_big, N, roff

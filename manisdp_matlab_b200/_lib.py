@@ -14,10 +14,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmanisdp_b200.so")
 
-ONLYUNITDIAG, UNITDIAG, UNITTRACE, GENERAL = 0, 1, 2, 3
+ONLYUNITDIAG, UNITDIAG, UNITTRACE, GENERAL, MULTIBLOCK = 0, 1, 2, 3, 4
 LAYOUT_ROWS, LAYOUT_COLS = 0, 1
 SLOT_Y, SLOT_YPROP, SLOT_G, SLOT_ETA, SLOT_R, SLOT_D, SLOT_HD, SLOT_U, SLOT_H = range(9)
-KIND_NAMES = {"onlyunitdiag": ONLYUNITDIAG, "unitdiag": UNITDIAG, "unittrace": UNITTRACE, "general": GENERAL}
+KIND_NAMES = {"onlyunitdiag": ONLYUNITDIAG, "unitdiag": UNITDIAG, "unittrace": UNITTRACE, "general": GENERAL,
+              "multiblock": MULTIBLOCK}
 
 _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
@@ -29,7 +30,8 @@ class Problem(C.Structure):
                 ("At_jc", _u64p), ("At_ir", _u64p), ("At_pr", _f64p),
                 ("b", _f64p), ("c_ir", _u64p), ("c_pr", _f64p), ("c_nnz", C.c_int64),
                 ("rank", C.c_int32), ("world", C.c_int32), ("row_begin", C.c_int64), ("row_end", C.c_int64),
-                ("nccl_unique_id", C.c_void_p), ("force_mode", C.c_int32), ("shard_layout", C.c_int32)]
+                ("nccl_unique_id", C.c_void_p), ("force_mode", C.c_int32), ("shard_layout", C.c_int32),
+                ("nblocks", C.c_int32), ("nob", C.c_int32), ("block_sizes", C.POINTER(C.c_int64))]
 
 
 class TrOptions(C.Structure):
@@ -116,6 +118,14 @@ SIGNATURES = {
     "manisdp_group_line_search": (C.c_int, [_H, _f64p]),
     "manisdp_get_index_split": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,
                                           C.POINTER(C.c_int64)]),
+    "manisdp_mb_set_Y": (C.c_int, [_H, _f64p, C.POINTER(C.c_int64)]),
+    "manisdp_mb_get_Y": (C.c_int, [_H, _f64p]),
+    "manisdp_mb_get_widths": (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    "manisdp_mb_rand_Y": (C.c_int, [_H, C.POINTER(C.c_int64), C.c_uint64]),
+    "manisdp_mb_kkt": (C.c_int, [_H, C.c_int32, C.POINTER(KktInfo), _f64p, C.POINTER(C.c_int32)]),
+    "manisdp_mb_get_block_eigs": (C.c_int, [_H, C.c_int32, _f64p, _f64p]),
+    "manisdp_mb_update": (C.c_int, [_H, C.c_double, C.c_int32, C.c_double, C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -163,7 +173,7 @@ class Handle:
     """Thin object wrapper over manisdp_t*; every method maps 1:1 onto a C-ABI call."""
 
     def __init__(self, kind, n, *, C_csc=None, At=None, b=None, c=None, device=0, rank=0, world=1,
-                 row_begin=0, row_end=None, nccl_id=None, force_mode=0, layout="rows"):
+                 row_begin=0, row_end=None, nccl_id=None, force_mode=0, layout="rows", block_sizes=None, nob=0):
         import scipy.sparse as sp
 
         self.lib = load()
@@ -179,6 +189,13 @@ class Handle:
         pb.shard_layout = {"rows": 0, "cols": 1}[layout]
         self.layout, self.rank, self.world = layout, rank, world
         keep = []
+        if pb.kind == MULTIBLOCK:  # K.s, K.nob of ManiSDP_multiblock.m:7
+            bs = np.ascontiguousarray(block_sizes, dtype=np.int64)
+            assert int(bs.sum()) == n, "n must equal sum(block_sizes)"
+            keep.append(bs)
+            pb.nblocks, pb.nob = len(bs), int(nob)
+            pb.block_sizes = bs.ctypes.data_as(C.POINTER(C.c_int64))
+            self.block_sizes, self.nob = [int(v) for v in bs], int(nob)
         if pb.kind == ONLYUNITDIAG:
             Cm = sp.csc_matrix(C_csc)
             Cm.sort_indices()
@@ -394,6 +411,78 @@ class Handle:
         s = Stats()
         self._ck(self.lib.manisdp_get_stats(self._h, C.byref(s)), "get_stats")
         return s
+
+    # -- multi-block handles (manisdp_mb_*): a point is a list of (n_i, p_i) arrays, one row per vertex of the block
+    def _i64(self, v):
+        a = np.ascontiguousarray(v, dtype=np.int64)
+        assert a.shape == (len(self.block_sizes),)
+        return a, a.ctypes.data_as(C.POINTER(C.c_int64))
+
+    def mb_set_Y(self, blocks):
+        assert len(blocks) == len(self.block_sizes)
+        p, pp = self._i64([np.asarray(B).shape[1] for B in blocks])
+        cat = np.concatenate([_as_f64(B).ravel() for B in blocks])
+        self._ck(self.lib.manisdp_mb_set_Y(self._h, _pf(cat), pp), "mb_set_Y")
+
+    def mb_widths(self):
+        p, pp = self._i64(np.zeros(len(self.block_sizes)))
+        self._ck(self.lib.manisdp_mb_get_widths(self._h, pp), "mb_get_widths")
+        return [int(v) for v in p]
+
+    def mb_get_Y(self):
+        p = self.mb_widths()
+        cat = np.empty(int(sum(n * q for n, q in zip(self.block_sizes, p))))
+        self._ck(self.lib.manisdp_mb_get_Y(self._h, _pf(cat)), "mb_get_Y")
+        out, o = [], 0
+        for n, q in zip(self.block_sizes, p):
+            out.append(cat[o:o + n * q].reshape(n, q).copy())
+            o += n * q
+        return out
+
+    def mb_rand_Y(self, p, seed=0):
+        _, pp = self._i64(p)
+        self._ck(self.lib.manisdp_mb_rand_Y(self._h, pp, seed), "mb_rand_Y")
+
+    def mb_split(self, A):
+        """(N, pmax) slot array -> list of (n_i, p_i) blocks at the current widths"""
+        out, r = [], 0
+        for n, q in zip(self.block_sizes, self.mb_widths()):
+            out.append(np.ascontiguousarray(A[r:r + n, :q]))
+            r += n
+        return out
+
+    def mb_join(self, blocks):
+        """list of (n_i, p_i) blocks -> (N, pmax) slot array (zero padded)"""
+        pmax = self.p
+        A = np.zeros((self.n, pmax))
+        r = 0
+        for B in blocks:
+            A[r:r + B.shape[0], :B.shape[1]] = B
+            r += B.shape[0]
+        return A
+
+    def mb_kkt(self, update_dual=1):
+        k = KktInfo()
+        t = len(self.block_sizes)
+        dinfs = np.empty(t)
+        nneg = np.empty(t, dtype=np.int32)
+        self._ck(self.lib.manisdp_mb_kkt(self._h, int(update_dual), C.byref(k), _pf(dinfs),
+                                         nneg.ctypes.data_as(C.POINTER(C.c_int32))), "mb_kkt")
+        return k, dinfs, nneg
+
+    def mb_block_eigs(self, blk, vectors=True):
+        n = self.block_sizes[blk]
+        vals = np.empty(n)
+        vecs = np.empty((n, n)) if vectors else None
+        self._ck(self.lib.manisdp_mb_get_block_eigs(self._h, blk, _pf(vals), None if vecs is None else _pf(vecs)),
+                 "mb_get_block_eigs")
+        return vals, vecs
+
+    def mb_update(self, theta, delta, alpha, line_search=0, min_facsize=2):
+        p, pp = self._i64(np.zeros(len(self.block_sizes)))
+        self._ck(self.lib.manisdp_mb_update(self._h, float(theta), int(delta), float(alpha), int(line_search),
+                                            int(min_facsize), pp), "mb_update")
+        return [int(v) for v in p]
 
 
 def nccl_unique_id() -> bytes:

@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
   const int gl = threadIdx.x % GS, nvec = ld / 2;
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
   const double s2z = (MF == MF_SPHERE) ? st->tmp[T_S] : 0.0;
+  const long long nob = (MF == MF_OBLIQUE) ? st->nob_rows : 0;
   double q[1] = {0.0};
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; row < nrows; row += ngroups) {
     const size_t rb = (size_t)row * ld;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
       }
     }
     if (MF == MF_OBLIQUE) {
-      dot = group_sum<GS>(dot, mask);
+      dot = rowsel(group_sum<GS>(dot, mask), row < nob);  // Euclidean block of a multi-block point: G = EG (:219-223)
       if (gl == 0) eGout[row] = dot;
     }
     if (MF == MF_SPHERE) dot = s2z;
@@ -396,6 +397,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
   const double shy = (MF == MF_SPHERE) ? st->tmp[T_S] : 0.0;
   const double twoz = (MF == MF_SPHERE) ? 2.0 * st->zsph[zslot] : 0.0;
+  const long long nob = (MF == MF_OBLIQUE) ? st->nob_rows : 0;
   double q[1] = {0.0};
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; row < nrows; row += ngroups) {
     const size_t rb = (size_t)row * ld;
@@ -415,8 +417,8 @@ __global__ void __launch_bounds__(MSDP_THREADS)
     }
     double mu = 0.0;
     if (MF == MF_OBLIQUE) {
-      dot = group_sum<GS>(dot, mask);
-      mu = YeG[row];
+      dot = rowsel(group_sum<GS>(dot, mask), row < nob);
+      mu = (row < nob) ? YeG[row] : 0.0;
     }
     if (MF == MF_SPHERE) {
       dot = shy;
@@ -496,6 +498,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
     k_rowdot(const double* __restrict__ Y, const double* __restrict__ T, double* __restrict__ zout, RtrState* st,
              double* partials, int64_t nrows, int ld, int slot) {
   __shared__ double sm[32];
+  const long long nob = st->nob_rows;
   const unsigned mask = group_mask<GS>();
   const int gl = threadIdx.x % GS, nvec = ld / 2;
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
         dot += a.x * b.x + a.y * b.y;
       }
     }
-    dot = group_sum<GS>(dot, mask);
+    dot = rowsel(group_sum<GS>(dot, mask), row < nob);  // multi-block: z only on the unit-diagonal blocks (:84-88)
     if (gl == 0) {
       if (zout) zout[row] = dot;
       q[0] += dot;
@@ -549,7 +552,22 @@ int msdp_affine_setup(manisdp_handle* h, const manisdp_problem* pb) {
   if (!pb->At_jc || !pb->At_ir || !pb->At_pr || !pb->b || !pb->c_pr)
     return msdp_fail(h, MANISDP_E_ARG, "affine kinds need At (CSC), b and c");
   const int64_t n = h->n, m = h->m;
-  const uint64_t nn = (uint64_t)n * (uint64_t)n;
+  const bool mb = (h->kind == MANISDP_MULTIBLOCK);
+  // rows of At / entries of c: n*n for one block, sum(n_i^2) -- the stacked vecs -- for a multi-block problem
+  const uint64_t nn = mb ? (uint64_t)h->mb_off2.back() : (uint64_t)n * (uint64_t)n;
+  // r -> (i, j) of the (embedded) matrix, in 64-bit integer arithmetic.  Multi-block: block k = the one whose range
+  // [off2_k, off2_k + n_k^2) holds r; inside it r - off2_k = b*n_k + a addresses X_k(a, b) (ManiSDP_multiblock.m:67-72).
+  auto split = [&](uint64_t r, int* i, int* j) {
+    if (!mb) {
+      *i = (int)(r % (uint64_t)n);
+      *j = (int)(r / (uint64_t)n);
+      return;
+    }
+    const size_t k = (size_t)(std::upper_bound(h->mb_off2.begin(), h->mb_off2.end(), (int64_t)r) - h->mb_off2.begin()) - 1;
+    const uint64_t loc = r - (uint64_t)h->mb_off2[k], nk = (uint64_t)h->mb_n[k];
+    *i = (int)((uint64_t)h->mb_roff[k] + loc % nk);
+    *j = (int)((uint64_t)h->mb_roff[k] + loc / nk);
+  };
   if (n >= (1ll << 31) || m >= (1ll << 31)) return msdp_fail(h, MANISDP_E_ARG, "n and m must be < 2^31");
   const uint64_t nnzA = pb->At_jc[m];
   if (nnzA >= (1ull << 31)) return msdp_fail(h, MANISDP_E_ARG, "nnz(At) must be < 2^31");
@@ -567,6 +585,7 @@ int msdp_affine_setup(manisdp_handle* h, const manisdp_problem* pb) {
   if (pb->force_mode & 2) s_dense = false;
   if (pb->force_mode & 4) a_dense = true;
   if (pb->force_mode & 8) a_dense = false;
+  if (mb) a_dense = s_dense = false;  // the block structure lives in the index lists; an N x N dense S would not
   if (a_dense) s_dense = true;
   if (s_dense && n > 40000) return msdp_fail(h, MANISDP_E_ARG, "dense S representation needs n <= 40000");
   h->a_mode = a_dense ? MODE_DENSE : MODE_SPARSE;
@@ -591,8 +610,7 @@ int msdp_affine_setup(manisdp_handle* h, const manisdp_problem* pb) {
   for (uint64_t e = 0; e < nnzA; ++e) {
     const uint64_t r = pb->At_ir[e];
     if (r >= nn) return msdp_fail(h, MANISDP_E_ARG, "At: row index out of range");
-    ei[(size_t)e] = (int)(r % (uint64_t)n);
-    ej[(size_t)e] = (int)(r / (uint64_t)n);
+    split(r, &ei[(size_t)e], &ej[(size_t)e]);
   }
   if (!a_dense) {
     ASparse& S = h->As;
@@ -708,12 +726,15 @@ int msdp_affine_setup(manisdp_handle* h, const manisdp_problem* pb) {
     std::vector<double> val(ent.size());
     for (auto& t : ent) {
       if (t.first >= nn) return msdp_fail(h, MANISDP_E_ARG, "c: index out of range");
-      rp[(size_t)(t.first % (uint64_t)n) + 1]++;
+      int ci, cj;
+      split(t.first, &ci, &cj);
+      rp[(size_t)ci + 1]++;
     }
     for (int64_t i = 0; i < n; ++i) rp[(size_t)i + 1] += rp[(size_t)i];
     std::vector<int> fill(rp.begin(), rp.end() - 1);
     for (auto& t : ent) {
-      const int i = (int)(t.first % (uint64_t)n), j = (int)(t.first / (uint64_t)n);
+      int i, j;
+      split(t.first, &i, &j);
       const int pos = fill[(size_t)i]++;
       col[(size_t)pos] = j;
       val[(size_t)pos] = t.second;

@@ -361,7 +361,7 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
 
 static int create_impl(manisdp_handle* h, const manisdp_problem* pb) {
   NvtxRange nvtx_range("manisdp:create");
-  if (pb->kind < MANISDP_ONLYUNITDIAG || pb->kind > MANISDP_GENERAL) return msdp_fail(h, MANISDP_E_ARG, "bad kind");
+  if (pb->kind < MANISDP_ONLYUNITDIAG || pb->kind > MANISDP_MULTIBLOCK) return msdp_fail(h, MANISDP_E_ARG, "bad kind");
   if (pb->n < 1) return msdp_fail(h, MANISDP_E_ARG, "n must be >= 1");
   h->kind = pb->kind;
   h->mf = (pb->kind == MANISDP_UNITTRACE) ? MF_SPHERE : (pb->kind == MANISDP_GENERAL ? MF_EUCLID : MF_OBLIQUE);
@@ -405,6 +405,10 @@ static int create_impl(manisdp_handle* h, const manisdp_problem* pb) {
   }
   CUDA_TRY(h, cudaMalloc((void**)&h->st, sizeof(RtrState)));
   CUDA_TRY(h, cudaMemset(h->st, 0, sizeof(RtrState)));
+  {  // per-row manifold switch of the oblique kernels: every row is a unit vector unless a multi-block setup says otherwise
+    const long long all_rows = 0x7fffffffffffffffll;
+    CUDA_TRY(h, cudaMemcpy(&h->st->nob_rows, &all_rows, sizeof(long long), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(h, cudaMallocHost((void**)&h->st_host, sizeof(RtrState)));
   memset(h->st_host, 0, sizeof(RtrState));
   CUDA_TRY(h, cudaMalloc((void**)&h->partials, sizeof(double) * MSDP_NQ * MSDP_MAX_BLOCKS));
@@ -421,6 +425,10 @@ static int create_impl(manisdp_handle* h, const manisdp_problem* pb) {
     h->s_mode = MODE_SPARSE;
     h->a_mode = MODE_NONE;
   } else {
+    if (h->kind == MANISDP_MULTIBLOCK) {
+      if (pb->world > 1) return msdp_fail(h, MANISDP_E_ARG, "multi-block handles are single-GPU (SURVEY 8e: small blocks, latency-bound)");
+      MSDP_TRY(msdp_mb_setup(h, pb));
+    }
     MSDP_TRY(msdp_affine_setup(h, pb));
   }
   return MANISDP_OK;
@@ -435,6 +443,7 @@ static void free_all(manisdp_handle* h) {
   msdp_dist_destroy(h);
   msdp_col_destroy(h);
   msdp_affine_free(h);
+  msdp_mb_free(h);
   double* arrs[] = {h->Ybuf[0], h->Ybuf[1], h->Gbuf[0], h->Gbuf[1], h->eta[0], h->eta[1], h->r, h->d, h->Hd,
                     h->Uslot, h->Hslot, h->gatherbuf, h->eG[0], h->eG[1], h->zdiag, h->partials, h->C.val,
                     h->eigvecs};

@@ -37,6 +37,9 @@ struct RtrState {
   int stop, j, maxinner, mininner, branch, eta_cur;
   int hv_count;
   unsigned int ticket;
+  // multi-block handles (multiblockmanifold.m:1-42): rows [0, nob_rows) are unit vectors (oblique blocks), the rows behind
+  // them are Euclidean.  Every other oblique handle keeps LLONG_MAX here (all rows oblique).
+  long long nob_rows;
 };
 
 struct Csr {  // row lists on the device (int32 indices; n, nnz < 2^31)
@@ -190,9 +193,25 @@ struct manisdp_handle {
   // escape step run once per outer iteration and used to pay two to four cudaMalloc / cudaFree pairs each
   void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t scratch_cap[4] = {0, 0, 0, 0};
+  // multi-block handles (multiblock.cu): block orders, row offsets (prefix sums of n_i), offsets into the stacked vec
+  // (prefix sums of n_i^2), current widths; n = mb_roff.back(); rows [0, mb_nob_rows) are unit vectors
+  std::vector<int64_t> mb_n, mb_roff, mb_off2, mb_p;
+  int mb_nob = 0;
+  int64_t mb_nob_rows = 0;
+  int* mb_rowblk = nullptr;              // N: block of each row (device)
+  int* mb_roff_dev = nullptr;            // t + 1: row offsets (device)
+  int* mb_pw = nullptr;                  // 4t ints: current widths, then work vectors of mb_update (device)
+  int mb_have_eigs = 0;                  // mb_evals / mb_evecs belong to the current point
+  std::vector<double> mb_evals;          // eigenvalues of every S{i} of the last mb_kkt, stacked by block (ascending)
+  std::vector<double> mb_evecs;          // eigenvectors, block i at mb_off2[i], row-major n_i x n_i (column k = k-th vector)
   std::string err;
 };
 int msdp_scratch(manisdp_handle* h, int slot, size_t bytes, void** out);  // api.cu
+// multiblock.cu
+int msdp_mb_setup(manisdp_handle* h, const manisdp_problem* pb);
+void msdp_mb_free(manisdp_handle* h);
+double msdp_mb_typicaldist(const manisdp_handle* h);
+double msdp_mb_dim(const manisdp_handle* h);
 
 // ---- tracing: one NVTX range per phase of the hot path (visible in Nsight Systems / ncu --nvtx; no cost when no
 // tool is attached: NVTX v3 is header-only and resolves its injection library lazily) -----------------------------

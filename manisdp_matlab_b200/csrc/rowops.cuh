@@ -22,6 +22,9 @@ __device__ __forceinline__ double group_sum(double v, unsigned mask) {
   return v;
 }
 
+// per-row manifold switch of multi-block points: the row multiplier of a Euclidean row is zero
+__device__ __forceinline__ double rowsel(double v, bool oblique_row) { return oblique_row ? v : 0.0; }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);

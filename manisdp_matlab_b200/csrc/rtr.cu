@@ -159,7 +159,9 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
   if (o) opt = *o;
   // defaults: trustregions.m:340-372
   double typicaldist;
-  if (h->mf == MF_OBLIQUE)
+  if (h->kind == MANISDP_MULTIBLOCK)
+    typicaldist = msdp_mb_typicaldist(h);  // multiblockmanifold.m:11-15
+  else if (h->mf == MF_OBLIQUE)
     typicaldist = M_PI * sqrt((double)h->n);  // ManiSDP_unitdiag.m:179
   else if (h->mf == MF_SPHERE)
     typicaldist = M_PI;  // spherefactory.m:111
@@ -169,6 +171,7 @@ int msdp_tr_solve(manisdp_handle* h, const manisdp_tr_options* o, manisdp_tr_inf
   if (opt.maxinner <= 0) {  // M.dim()
     double dim = (h->mf == MF_OBLIQUE) ? (double)(h->p - 1) * h->n
                                        : (h->mf == MF_SPHERE ? (double)h->n * h->p - 1 : (double)h->n * h->p);
+    if (h->kind == MANISDP_MULTIBLOCK) dim = msdp_mb_dim(h);  // multiblockmanifold.m:3
     opt.maxinner = (int)fmin(dim, 2.0e9);
     if (opt.maxinner < 1) opt.maxinner = 1;
   }

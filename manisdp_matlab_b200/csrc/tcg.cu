@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_tcg_dir(VecPtrs v, RtrState* s
   const double beta = st->beta;
   const double* __restrict__ Y = st->pt ? v.Y1 : v.Y0;
   const double sph = (MF == MF_SPHERE) ? (st->y_r + beta * st->y_d) : 0.0;
+  const long long nob = (MF == MF_OBLIQUE) ? st->nob_rows : 0;
   const unsigned mask = group_mask<GS>();
   const int gl = threadIdx.x % GS;
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_tcg_dir(VecPtrs v, RtrState* s
         }
       }
     }
-    if (MF == MF_OBLIQUE) dot = group_sum<GS>(dot, mask);  // ManiSDP_unitdiag.m:181
+    if (MF == MF_OBLIQUE) dot = rowsel(group_sum<GS>(dot, mask), row < nob);  // ManiSDP_unitdiag.m:181 / projc.cpp:34-48
     if (MF == MF_SPHERE) dot = sph;                        // spherefactory.m:113
 #pragma unroll
     for (int t = 0; t < VPL; ++t) {
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
   const double* __restrict__ Y = from_state ? (st->pt ? v.Y1 : v.Y0) : Yin;
   const double* __restrict__ E = from_state ? (st->eta_cur ? v.eta1 : v.eta0) : eta;
   double* __restrict__ out = from_state ? (st->pt ? v.Y0 : v.Y1) : dst;
+  const long long nob = (MF == MF_OBLIQUE) ? st->nob_rows : 0;
   const unsigned mask = group_mask<GS>();
   const int gl = threadIdx.x % GS;
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
     double scale = 1.0;
     if (MF == MF_OBLIQUE) {
       ss = group_sum<GS>(ss, mask);
-      scale = 1.0 / sqrt(ss);
+      scale = (row < nob) ? 1.0 / sqrt(ss) : 1.0;  // Euclidean blocks of a multi-block point: Y + eta (retrc.cpp)
     }
     if (MF == MF_SPHERE) q[0] += ss;
 #pragma unroll
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
 template <int GS, int VPL, int MF>
 __global__ void __launch_bounds__(MSDP_THREADS)
     k_project(const double* Y, const double* src, double* dst, RtrState* st, int64_t nrows, int ld, int use_tmp0) {
+  const long long nob = (MF == MF_OBLIQUE) ? st->nob_rows : 0;
   const unsigned mask = group_mask<GS>();
   const int gl = threadIdx.x % GS;
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
         dot += x[t].x * y[t].x + x[t].y * y[t].y;
       }
     }
-    if (MF == MF_OBLIQUE) dot = group_sum<GS>(dot, mask);
+    if (MF == MF_OBLIQUE) dot = rowsel(group_sum<GS>(dot, mask), row < nob);
     if (MF == MF_SPHERE) dot = use_tmp0 ? st->tmp[0] : 0.0;
 #pragma unroll
     for (int t = 0; t < VPL; ++t) {

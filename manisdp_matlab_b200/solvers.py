@@ -267,3 +267,111 @@ def ManiSDP(At, b, c, K, options=None):
     """src/primal/ManiSDP.m:6"""
     return _affine_driver("general", At, b, c, K, options)
 
+
+
+# ManiSDP_multiblock.m:10-27
+MB_DEFAULTS = dict(min_facsize=2, p0=None, AL_maxiter=1000, gama=2, sigma0=1e-1, sigma_min=1e-2, sigma_max=1e7,
+                   tol=1e-8, theta=1e-2, delta=8, alpha=0.1, tolgradnorm=1e-8, TR_maxinner=20, TR_maxiter=4,
+                   tau1=1e1, tau2=1e1, line_search=0)
+
+
+def ManiSDP_multiblock(At, b, c, K, options=None):
+    """min <C,X> s.t. A(X) = b, X in S_+^{n_1 x ... x n_t}, diag(X_i) = 1 for i <= K.nob
+    (src/primal/ManiSDP_multiblock.m:7).  K['s']: block orders, K['nob']: number of leading unit-diagonal blocks.
+    options['Y0'] (extension): list of (n_i, p_i) arrays.  Returns X and data['S'] as lists of blocks."""
+    import scipy.sparse as sp
+
+    o = dict(MB_DEFAULTS)
+    o.update(options or {})
+    for k_, v_ in dict(seed=0, verbose=True, use_graph=1, device=0).items():
+        o.setdefault(k_, v_)
+    nset = [int(v) for v in np.atleast_1d(K["s"])]
+    nb = len(nset)
+    nob = int(K.get("nob", 0))
+    N = int(sum(nset))
+    At = sp.csc_matrix(At)
+    bd = np.asarray(b.todense()).ravel() if sp.issparse(b) else np.asarray(b, dtype=np.float64).ravel()
+    m = At.shape[1]
+    _say(o, "ManiSDP is starting...")
+    _say(o, f"SDP size: n = {max(nset)}, m = {m}")
+    p0 = o["p0"] if o["p0"] is not None else [1] * nb  # :12
+    p = list(nset)  # :33-39
+    for i in range(nb):
+        if nset[i] >= o["min_facsize"]:
+            p[i] = int(p0[i])
+    sigma, gama = float(o["sigma0"]), float(o["gama"])
+    data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[], tr_seconds=0.0)
+    phase = dict(create=0.0, line_search=0.0, tr_solve=0.0, kkt=0.0, update=0.0)
+    t0 = time.perf_counter()
+    gap0 = pinf0 = dinf0 = None
+
+    def timed(name, fn, *a):
+        t1 = time.perf_counter()
+        r_ = fn(*a)
+        phase[name] += time.perf_counter() - t1
+        return r_
+
+    with _lib.Handle("multiblock", N, At=At, b=bd, c=c, device=o["device"], block_sizes=nset, nob=nob) as h:
+        h.set_dual(np.zeros(m), sigma)
+        if o.get("Y0") is not None:
+            h.mb_set_Y([np.asarray(B, dtype=np.float64) for B in o["Y0"]])
+        else:
+            h.mb_rand_Y(p, int(o["seed"]))  # trustregions.m:390-392 -> M.rand() (randc.cpp)
+        phase["create"] = time.perf_counter() - t0
+        staged = False
+        for it in range(1, int(o["AL_maxiter"]) + 1):
+            p = h.mb_widths()
+            data["fac_size"].append(list(p))
+            if staged:
+                timed("line_search", h.line_search)  # :62-64
+            info = timed("tr_solve", h.tr_solve, o["TR_maxiter"], o["TR_maxinner"], o["tolgradnorm"], o["use_graph"])
+            data["hv_count"] += info.hv_count
+            data["tr_iters"] += info.iters
+            data["tr_seconds"] += info.seconds
+            gradnorm = info.gradnorm
+            k, dinfs, nneg = timed("kkt", h.mb_kkt, 1)  # :66-97
+            obj, gap, pinf, dinf = k.obj, k.gap, k.pinf, k.dinf
+            _say(o, f"Iter {it}, obj:{obj:0.8f}, gap:{gap:0.1e}, pinf:{pinf:0.1e}, dinf:{dinf:0.1e}, "
+                    f"gradnorm:{gradnorm:0.1e}, p_max:{max(p)}, sigma:{sigma:0.3f}, time:{time.perf_counter()-t0:0.2f}s")
+            eta = max(gap, pinf, dinf)
+            if eta < o["tol"]:
+                _say(o, "Optimality is reached!")
+                break
+            if it % 50 == 0:  # :103-113
+                if it > 100 and gap > gap0 and pinf > pinf0 and dinf > dinf0:
+                    data["status"] = 2
+                    _say(o, "Slow progress!")
+                    break
+                gap0, pinf0, dinf0 = gap, pinf, dinf
+            if it == int(o["AL_maxiter"]):
+                break
+            timed("update", h.mb_update, o["theta"], o["delta"], o["alpha"], int(o["line_search"]),
+                  int(o["min_facsize"]))  # :114-153
+            staged = int(o["line_search"]) == 1
+            if pinf < o["tau1"] * gradnorm:  # :154-158
+                sigma = max(sigma / gama, o["sigma_min"])
+            elif pinf > o["tau2"] * gradnorm:
+                sigma = min(sigma * gama, o["sigma_max"])
+            h.set_sigma(sigma)
+        Y = h.mb_get_Y()
+        y, _ = h.get_dual()
+        st = h.stats()
+        data["launches"] = st.launches_total
+        data["phase_seconds"] = phase
+    X = [Yi @ Yi.T for Yi in Y]
+    cd = np.asarray(c.todense()).ravel() if sp.issparse(c) else np.asarray(c, dtype=np.float64).ravel()
+    cy = cd - At @ y
+    S, o2 = [], 0
+    for i, ni in enumerate(nset):
+        Si = cy[o2:o2 + ni * ni].reshape(ni, ni, order="F")
+        if i < nob:
+            Si = Si - np.diag(np.sum(X[i] * Si, axis=0))
+        S.append(Si)
+        o2 += ni * ni
+    data.update(X=X, y=y, S=S, gap=gap, pinf=pinf, dinf=dinf, gradnorm=gradnorm, time=time.perf_counter() - t0, Y=Y,
+                iters=it, obj=obj, sigma=sigma, dinfs=dinfs)
+    if data["status"] == 0 and eta > o["tol"]:
+        data["status"] = 1
+        _say(o, "Iteration maximum is reached!")
+    _say(o, f"ManiSDP: optimum = {obj:0.8f}, time = {data['time']:0.2f}s")
+    return X, obj, data

@@ -6,6 +6,7 @@ CPU restatement (NumPy/SciPy FP64, dense X / dense eig exactly as the reference 
   * src/primal/ManiSDP_unitdiag.m       (closures :152-171, outer loop :51-113, line search :131-150)
   * src/primal/ManiSDP_unittrace.m      (closures :156-177, outer loop :52-117)
   * src/primal/ManiSDP.m                (closures :149-165, outer loop :52-113)
+  * src/primal/ManiSDP_multiblock.m     (closures :203-247, outer loop :60-160, line search :180-201)
 
 driving oracle/manopt_rtr.py in place of Manopt's trustregions.  It is the parity yardstick for the
 CUDA engine and the CPU baseline timed by bench.py; nothing in the product path imports it.
@@ -35,7 +36,7 @@ import time
 import numpy as np
 import scipy.sparse as sp
 
-from .manopt_rtr import Euclid, ObliqueT, Sphere, trustregions
+from .manopt_rtr import Cells, Euclid, MultiBlock, ObliqueT, Sphere, trustregions
 
 # option defaults, SURVEY.md Appendix B (source lines cited there)
 DEFAULTS = {
@@ -363,3 +364,214 @@ def ManiSDP_unittrace(At, b, c, K, options=None):
 def ManiSDP(At, b, c, K, options=None):
     """[X, obj, data] of src/primal/ManiSDP.m:6."""
     return _affine_driver("general", At, b, c, K, options)
+
+
+# --------------------------------------------------------------------------------------------
+# multi-block driver
+# --------------------------------------------------------------------------------------------
+MB_DEFAULTS = dict(min_facsize=2, p0=None, AL_maxiter=1000, gama=2, sigma0=1e-1, sigma_min=1e-2,
+                   sigma_max=1e7, tol=1e-8, theta=1e-2, delta=8, alpha=0.1, tolgradnorm=1e-8,
+                   TR_maxinner=20, TR_maxiter=4, tau1=1e1, tau2=1e1, line_search=0)  # :10-27
+
+
+class MultiblockProblem:
+    """Closures of ManiSDP_multiblock.m:203-247 on f(Y) = c'x + sigma/2 |A x - b - y/sigma|^2 with
+    x = [vec(Y_1 Y_1'); ...; vec(Y_t Y_t')]  (block i: (n_i, p_i), row layout)."""
+
+    def __init__(self, At, b, c, nset, pset, nob, y, sigma):
+        self.At, self.A = At, At.T.tocsr()
+        self.b, self.c, self.y, self.sigma = b, c, y, sigma
+        self.n, self.nob = [int(v) for v in nset], int(nob)
+        self.off = np.concatenate([[0], np.cumsum([v * v for v in self.n])]).astype(np.int64)
+        self.M = MultiBlock(pset, nset, nob)
+
+    def xvec(self, Y):  # :205-209
+        return np.concatenate([_vec(Yi @ Yi.T) for Yi in Y])
+
+    def blocks(self, v):
+        return [_mat(v[self.off[i]:self.off[i + 1]], ni) for i, ni in enumerate(self.n)]
+
+    def co(self, Y):  # :170-178
+        x = self.xvec(Y)
+        Axb = self.A @ x - self.b - self.y / self.sigma
+        return float(self.c @ x + 0.5 * self.sigma * (Axb @ Axb))
+
+    def cost(self, Y):  # :203-212
+        x = self.xvec(Y)
+        self.Axb = self.A @ x - self.b - self.y / self.sigma
+        return float(self.c @ x + 0.5 * self.sigma * (self.Axb @ self.Axb))
+
+    def accept(self, ok):
+        pass
+
+    def grad(self, Y):  # :214-226
+        self.S = self.blocks(self.c + self.sigma * (self.At @ self.Axb))
+        G, self.eG = [], []
+        for i, Yi in enumerate(Y):
+            Gi = 2 * (self.S[i] @ Yi)
+            if i < self.nob:
+                e = np.sum(Yi * Gi, axis=1, keepdims=True)
+                Gi = Gi - Yi * e
+            else:
+                e = None
+            self.eG.append(e)
+            G.append(Gi)
+        return Cells(G)
+
+    def hess(self, Y, U):  # :228-247  (T = Y'*U of the p x n layout: T(a,b) = <Y_a, U_b>)
+        YU = np.concatenate([_vec(Yi @ Ui.T) for Yi, Ui in zip(Y, U)])
+        AyU = self.blocks(self.At @ (self.A @ YU))
+        H = []
+        for i, (Yi, Ui) in enumerate(zip(Y, U)):
+            Hi = 2 * (self.S[i] @ Ui) + 4 * self.sigma * (AyU[i] @ Yi)
+            if i < self.nob:
+                Hi = Hi - Yi * np.sum(Yi * Hi, axis=1, keepdims=True) - Ui * self.eG[i]
+            H.append(Hi)
+        return Cells(H)
+
+
+def _mb_normalize(Y, nob):
+    return Cells([Yi / np.sqrt(np.sum(Yi * Yi, axis=1, keepdims=True)) if i < nob else Yi
+                  for i, Yi in enumerate(Y)])
+
+
+def _mb_line_search(co, Y, U, nob, literal_first_trial=False):
+    """ManiSDP_multiblock.m:180-201.  The reference stacks [Y{i}; alpha*U{i}] (2p x n): because the
+    rows of Y that U fills are zero, the Gram matrix -- hence the cost and every later iterate --
+    equals that of Y + alpha*U, which is what is formed here so that the width stays p.
+    `literal_first_trial`: line :184 builds the FIRST candidate from the empty nY (`[nY{i};
+    alpha*U{i}]`), i.e. U alone; True reproduces that, False (default) starts from Y + U like the
+    single-block drivers (ManiSDP_unitdiag.m:142)."""
+    alpha = 1.0
+    cost0 = co(Y)
+    if literal_first_trial:
+        nY = _mb_normalize(Cells([alpha * Ui for Ui in U]), nob)
+    else:
+        nY = _mb_normalize(Y + alpha * U, nob)
+    k = 1
+    while k <= 15 and co(nY) - cost0 > -1e-3:
+        alpha *= 0.8
+        nY = _mb_normalize(Y + alpha * U, nob)
+        k += 1
+    return nY
+
+
+def ManiSDP_multiblock(At, b, c, K, options=None):
+    """[X, obj, data] of src/primal/ManiSDP_multiblock.m:7 (K['s'] block orders, K['nob'] leading
+    unit-diagonal blocks)."""
+    o = dict(MB_DEFAULTS)
+    o.update(options or {})
+    o.setdefault("seed", 0)
+    o.setdefault("verbose", False)
+    n = [int(v) for v in np.atleast_1d(K["s"])]
+    nb = len(n)
+    nob = int(K.get("nob", 0))
+    At = sp.csc_matrix(At)
+    b = np.asarray(b.todense()).ravel() if sp.issparse(b) else np.asarray(b, dtype=np.float64).ravel()
+    c = np.asarray(c.todense()).ravel() if sp.issparse(c) else np.asarray(c, dtype=np.float64).ravel()
+    A = At.T.tocsr()
+    p0 = o["p0"] if o["p0"] is not None else [1] * nb
+    p = list(n)  # :33-39
+    for i in range(nb):
+        if n[i] >= o["min_facsize"]:
+            p[i] = int(p0[i])
+    sigma, gama = o["sigma0"], o["gama"]
+    y = np.zeros(len(b))
+    normb = 1 + np.linalg.norm(b)
+    rng = np.random.default_rng(o["seed"])
+    Y = o.get("Y0")
+    if Y is not None:
+        Y = Cells([np.array(Yi, dtype=np.float64) for Yi in Y])
+        p = [Yi.shape[1] for Yi in Y]
+    U = None
+    data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[])
+    t0 = time.perf_counter()
+    gap0 = pinf0 = dinf0 = None
+    off = np.concatenate([[0], np.cumsum([v * v for v in n])]).astype(np.int64)
+    for it in range(1, o["AL_maxiter"] + 1):
+        data["fac_size"].append(list(p))
+        prob = MultiblockProblem(At, b, c, n, p, nob, y, sigma)  # :61
+        if Y is None:
+            Y = prob.M.rand(rng)
+        if U is not None:
+            Y = _mb_line_search(prob.co, Y, U, nob, o.get("literal_first_trial", False))  # :62-64
+        res = trustregions(prob, Y, maxiter=o["TR_maxiter"], maxinner=o["TR_maxinner"],
+                           tolgradnorm=o["tolgradnorm"])  # :65
+        Y = res.x
+        data["hv_count"] += res.hv_count
+        data["tr_iters"] += len(res.info) - 1
+        gradnorm = res.info[-1].gradnorm
+        X = [Yi @ Yi.T for Yi in Y]  # :67-72
+        x = np.concatenate([_vec(Xi) for Xi in X])
+        obj = float(c @ x)
+        Axb = A @ x - b
+        pinf = float(np.linalg.norm(Axb)) / normb
+        y = y - sigma * Axb
+        cy = c - At @ y
+        by = float(b @ y)
+        dinfs = np.zeros(nb)
+        S, dS, vS = [], [], []
+        for i in range(nb):  # :81-93
+            Si = _mat(cy[off[i]:off[i + 1]], n[i])
+            if i < nob:
+                z = np.sum(X[i] * Si, axis=0)
+                by += float(z.sum())
+                Si = Si - np.diag(z)
+            d, v = np.linalg.eigh(Si)
+            S.append(Si)
+            dS.append(d)
+            vS.append(v)
+            dinfs[i] = max(0.0, -d[0]) / (1 + abs(d[-1]))
+        dinf = float(dinfs.max())
+        gap = abs(obj - by) / (abs(by) + abs(obj) + 1)
+        if o["verbose"]:
+            print(f"Iter {it}, obj:{obj:0.8f}, gap:{gap:0.1e}, pinf:{pinf:0.1e}, dinf:{dinf:0.1e}, "
+                  f"gradnorm:{gradnorm:0.1e}, p_max:{max(p)}, sigma:{sigma:0.3f}, "
+                  f"time:{time.perf_counter()-t0:0.2f}s")
+        eta = max(gap, pinf, dinf)
+        if eta < o["tol"]:
+            break
+        if it % 50 == 0:  # :103-113
+            if it > 100 and gap > gap0 and pinf > pinf0 and dinf > dinf0:
+                data["status"] = 2
+                break
+            gap0, pinf0, dinf0 = gap, pinf, dinf
+        Yl = list(Y.b)
+        Ul = [None] * nb
+        for i in range(nb):  # :114-153
+            if n[i] < o["min_facsize"]:
+                if o["line_search"] == 1:
+                    Ul[i] = np.zeros_like(Yl[i])
+                continue
+            if p[i] > 1:
+                Us, e, _ = np.linalg.svd(Yl[i], full_matrices=False)
+                r = int(np.sum(e >= o["theta"] * e[0]))
+                if r == 0:
+                    r = 1
+                if r < p[i]:
+                    Yl[i] = Us[:, :r] * e[:r]
+                    p[i] = r
+            nneg = int(np.sum(dS[i] < 0))
+            nne = max(min(nneg, o["delta"]), 1) if i < nob else min(nneg, o["delta"])
+            if p[i] + nne > n[i]:
+                nne = 0
+            V = vS[i][:, :nne]
+            if o["line_search"] == 1:
+                Ul[i] = np.hstack([np.zeros((n[i], p[i])), V])
+                Yl[i] = np.hstack([Yl[i], np.zeros((n[i], nne))])
+            else:
+                Yl[i] = np.hstack([Yl[i], o["alpha"] * V])
+                if i < nob:
+                    Yl[i] = Yl[i] / np.sqrt(np.sum(Yl[i] * Yl[i], axis=1, keepdims=True))
+            p[i] += nne
+        Y = Cells(Yl)
+        U = Cells(Ul) if o["line_search"] == 1 else None
+        if pinf < o["tau1"] * gradnorm:  # :154-158
+            sigma = max(sigma / gama, o["sigma_min"])
+        elif pinf > o["tau2"] * gradnorm:
+            sigma = min(sigma * gama, o["sigma_max"])
+    data.update(X=X, y=y, S=S, gap=gap, pinf=pinf, dinf=dinf, gradnorm=gradnorm,
+                time=time.perf_counter() - t0, Y=Y, iters=it, obj=obj, sigma=sigma, dinfs=dinfs)
+    if data["status"] == 0 and eta > o["tol"]:
+        data["status"] = 1
+    return X, obj, data

@@ -293,3 +293,99 @@ def trustregions(problem, x, maxiter=1000, maxinner=None, tolgradnorm=1e-6, mini
     res.x = x
     res.cost = fx
     return res
+
+
+# --------------------------------------------------------------------------------------------
+# product manifold of the multi-block driver
+# --------------------------------------------------------------------------------------------
+class Cells:
+    """A MATLAB cell array of matrices with the arithmetic `lincombc.cpp:21-66` provides
+    (a1*u1, a1*u1 + a2*u2), so that `tCG` / `trustregions` above run unchanged on a product point.
+    Block i is an (n_i, p_i) array (row layout, see the module docstring)."""
+
+    __array_ufunc__ = None  # NumPy scalars on the left defer to __rmul__
+
+    def __init__(self, blocks):
+        self.b = list(blocks)
+
+    def __len__(self):
+        return len(self.b)
+
+    def __getitem__(self, i):
+        return self.b[i]
+
+    def __iter__(self):
+        return iter(self.b)
+
+    def __add__(self, o):
+        return Cells([x + y for x, y in zip(self.b, o.b)])
+
+    def __sub__(self, o):
+        return Cells([x - y for x, y in zip(self.b, o.b)])
+
+    def __mul__(self, a):
+        return Cells([x * float(a) for x in self.b])
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return Cells([-x for x in self.b])
+
+    def copy(self):
+        return Cells([x.copy() for x in self.b])
+
+
+class MultiBlock:
+    """src/basicfunction/multiblockmanifold.m:1-42: the first `nob` blocks are transposed oblique
+    manifolds (unit rows here), the others Euclidean.
+
+    The manifold operations are MEX files in the reference (src/C-files/{innerc,projc,retrc,
+    lincombc,randc,zerovecc}.cpp).  Two of the committed sources are older than the .m call sites
+    (retrc.cpp takes 3 arguments and normalises every block, multiblockmanifold.m:24 passes 4;
+    projc.cpp:34-43 subtracts ONE scalar <X_i,U_i> per block instead of one per unit vector).  This
+    restatement follows the .m call sites and the closures of ManiSDP_multiblock.m:214-247, which
+    use the per-vector form (`Y{i}.*sum(Y{i}.*H{i})`); on the tangent inputs tCG passes to M.proj
+    (tCG.m:273,283) the two forms of projc agree to rounding because every per-vector product is
+    already zero."""
+
+    name = "multiblock"
+
+    def __init__(self, pset, nset, nob):
+        self.p, self.n, self.nob = [int(v) for v in pset], [int(v) for v in nset], int(nob)
+
+    def dim(self):  # :3
+        return sum((p - 1) * n for p, n in zip(self.p[:self.nob], self.n[:self.nob])) + \
+            sum(p * n for p, n in zip(self.p[self.nob:], self.n[self.nob:]))
+
+    def typicaldist(self):  # :11-15
+        return math.sqrt(math.pi * sum(self.n[:self.nob]) +
+                         sum(p * n for p, n in zip(self.p[self.nob:], self.n[self.nob:])))
+
+    def inner(self, x, a, b):  # innerc.cpp:20-32
+        return float(sum(np.vdot(u, v) for u, v in zip(a, b)))
+
+    def norm(self, x, a):
+        return math.sqrt(self.inner(x, a, a))
+
+    def proj(self, x, u):  # projc.cpp:19-56 (per unit vector, see the class docstring)
+        return Cells([ui - xi * np.sum(xi * ui, axis=1, keepdims=True) if i < self.nob else ui.copy()
+                      for i, (xi, ui) in enumerate(zip(x, u))])
+
+    tangent = proj
+
+    def retr(self, x, d):  # retrc.cpp:24-47 with the nob argument of multiblockmanifold.m:24
+        out = []
+        for i, (xi, di) in enumerate(zip(x, d)):
+            y = xi + di
+            out.append(y / np.sqrt(np.sum(y * y, axis=1, keepdims=True)) if i < self.nob else y)
+        return Cells(out)
+
+    def rand(self, rng):  # randc.cpp:52-80
+        out = []
+        for i, (p, n) in enumerate(zip(self.p, self.n)):
+            x = rng.standard_normal((n, p))
+            out.append(x / np.sqrt(np.sum(x * x, axis=1, keepdims=True)) if i < self.nob else x)
+        return Cells(out)
+
+    def zerovec(self, x):
+        return Cells([np.zeros_like(xi) for xi in x])

@@ -1,0 +1,299 @@
+"""GPU parity tests of the multi-block driver (src/primal/ManiSDP_multiblock.m:60-249,
+src/basicfunction/multiblockmanifold.m:1-42, src/C-files/{projc,retrc,innerc,lincombc,randc}.cpp) through the C ABI
+(manisdp_mb_* + the shared closure / solver entry points), against oracle/manisdp_ref.py::ManiSDP_multiblock."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# (block orders, nob, m, seed) of instances.generators.multiblock_random on which the oracle reaches 1e-8
+CASES = [([6, 4, 5, 3], 0, 4, 1), ([6, 4, 5, 3], 2, 4, 2), ([8, 6, 7], 3, 6, 3), ([8, 6, 7, 2], 2, 5, 4)]
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(1e-300, np.linalg.norm(b))
+
+
+def _instance(case):
+    from instances import generators as G
+    ns, nob, m, seed = case
+    return G.multiblock_random(ns, nob, m, seed)
+
+
+def _point(ns, nob, widths, rng):
+    Y = []
+    for i, (n, p) in enumerate(zip(ns, widths)):
+        B = rng.standard_normal((n, p))
+        if i < nob:
+            B /= np.linalg.norm(B, axis=1, keepdims=True)
+        Y.append(B)
+    return Y
+
+
+def _handle(At, b, c, K, **kw):
+    from manisdp_matlab_b200 import Handle
+    ns = [int(v) for v in K["s"]]
+    return Handle("multiblock", int(sum(ns)), At=At, b=b, c=c, block_sizes=ns, nob=int(K["nob"]), **kw)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("widths", ["ones", "ragged"])
+def test_multiblock_closures_match_oracle(case, widths):
+    """cost / grad / hess of ManiSDP_multiblock.m:203-247 and the manifold operations at a random point whose blocks
+    have different widths, with a non-trivial dual vector and penalty."""
+    from oracle.manisdp_ref import MultiblockProblem
+    from oracle.manopt_rtr import Cells
+    At, b, c, K = _instance(case)
+    ns, nob = K["s"], K["nob"]
+    rng = np.random.default_rng(17)
+    p = [1] * len(ns) if widths == "ones" else [min(n, 1 + (3 * i + 2) % 5) for i, n in enumerate(ns)]
+    Y = _point(ns, nob, p, rng)
+    y = 0.3 * rng.standard_normal(At.shape[1])
+    sigma = 0.7
+    ora = MultiblockProblem(At.tocsc(), b, c, ns, p, nob, y, sigma)
+    Yc = Cells(Y)
+    f0 = ora.cost(Yc)
+    g0 = ora.grad(Yc)
+    U = ora.M.proj(Yc, Cells([rng.standard_normal(B.shape) for B in Y]))
+    H0 = ora.hess(Yc, U)
+    E = Cells([0.3 * rng.standard_normal(B.shape) for B in Y])
+    R0 = ora.M.retr(Yc, E)
+    with _handle(At, b, c, K) as h:
+        st = h.stats()
+        assert (st.s_mode, st.a_mode) == (1, 1)  # sparse representation: nothing of size N x N
+        h.set_dual(y, sigma)
+        h.mb_set_Y(Y)
+        assert h.mb_widths() == p
+        for Ba, Bb in zip(h.mb_get_Y(), Y):
+            assert np.array_equal(Ba, Bb)
+        f = h.cost()
+        G, gn = h.grad()
+        Hd = h.hess(h.mb_join(U.b))
+        Pd = h.project(h.mb_join(E.b))
+        Rd = h.retract(h.mb_join(E.b))
+        # the columns beyond p_i stay exactly zero
+        full = np.zeros((h.n, h.p), dtype=bool)
+        r = 0
+        for n, q in zip(ns, p):
+            full[r:r + n, :q] = True
+            r += n
+        for A in (G, Hd, Pd, Rd):
+            assert np.all(A[~full] == 0.0)
+        Gs, Hs, Ps, Rs = h.mb_split(G), h.mb_split(Hd), h.mb_split(Pd), h.mb_split(Rd)
+    assert abs(f - f0) <= 1e-12 * max(1.0, abs(f0))
+    P0 = ora.M.proj(Yc, E)
+    for i in range(len(ns)):
+        assert _rel(Gs[i], g0[i]) < 1e-12
+        assert _rel(Hs[i], H0[i]) < 1e-11
+        assert _rel(Ps[i], P0[i]) < 1e-13
+        assert _rel(Rs[i], R0[i]) < 1e-13
+    assert abs(gn - ora.M.norm(Yc, g0)) <= 1e-12 * max(1.0, gn)
+
+
+def test_multiblock_index_split_is_exact():
+    """row r of At -> (block, i, j) -> (row, column) of the embedded matrix, read back as integers"""
+    At, b, c, K = _instance(([5, 3, 4, 1, 2], 2, 9, 11))
+    ns = K["s"]
+    Atc = At.tocsc()
+    Atc.sort_indices()
+    off2 = np.concatenate([[0], np.cumsum([n * n for n in ns])])
+    roff = np.concatenate([[0], np.cumsum(ns)])
+    r = Atc.indices.astype(np.int64)
+    blk = np.searchsorted(off2, r, side="right") - 1
+    loc = r - off2[blk]
+    nb = np.asarray(ns)[blk]
+    with _handle(At, b, c, K) as h:
+        i, j = h.index_split()
+    assert np.array_equal(i, roff[blk] + loc % nb)
+    assert np.array_equal(j, roff[blk] + loc // nb)
+
+
+@pytest.mark.parametrize("case", CASES[1:3])
+@pytest.mark.parametrize("use_graph", [1, 0])
+def test_multiblock_tr_iterates_match_oracle(case, use_graph):
+    """trustregions + tCG on the product manifold: accept pattern, inner counts and stop codes identical"""
+    from oracle.manisdp_ref import MultiblockProblem
+    from oracle.manopt_rtr import Cells, trustregions
+    At, b, c, K = _instance(case)
+    ns, nob = K["s"], K["nob"]
+    rng = np.random.default_rng(5)
+    p = [min(n, 2 + i % 3) for i, n in enumerate(ns)]
+    Y0 = _point(ns, nob, p, rng)
+    y = 0.1 * rng.standard_normal(At.shape[1])
+    sigma = 2.0
+    ora = MultiblockProblem(At.tocsc(), b, c, ns, p, nob, y, sigma)
+    res = trustregions(ora, Cells([B.copy() for B in Y0]), maxiter=6, maxinner=15, tolgradnorm=1e-10)
+    with _handle(At, b, c, K) as h:
+        h.set_dual(y, sigma)
+        h.mb_set_Y(Y0)
+        info = h.tr_solve(maxiter=6, maxinner=15, tolgradnorm=1e-10, use_graph=use_graph)  # Delta_bar: M.typicaldist()
+        log = h.tr_log()
+        Yd = h.mb_get_Y()
+    assert [r.numinner for r in log] == [r.numinner for r in res.info]
+    assert [r.accepted for r in log] == [int(r.accepted) for r in res.info]
+    assert [r.stop_inner for r in log] == [r.stop_inner for r in res.info]
+    assert abs(log[0].Delta - ora.M.typicaldist() / 8) <= 1e-14 * ora.M.typicaldist()
+    assert abs(info.cost - res.cost) <= 1e-9 * max(1.0, abs(res.cost))
+    for i in range(len(ns)):
+        assert _rel(Yd[i], res.x[i]) < 1e-7
+
+
+@pytest.mark.parametrize("case", CASES[:3])
+def test_multiblock_kkt_matches_dense_formulas(case):
+    """ManiSDP_multiblock.m:66-97 against a dense per-block NumPy evaluation (eig of every S{i})"""
+    At, b, c, K = _instance(case)
+    ns, nob = K["s"], K["nob"]
+    rng = np.random.default_rng(3)
+    p = [min(n, 2 + i % 2) for i, n in enumerate(ns)]
+    Y = _point(ns, nob, p, rng)
+    y = 0.05 * rng.standard_normal(At.shape[1])
+    sigma = 3.0
+    X = [B @ B.T for B in Y]
+    x = np.concatenate([Xi.reshape(-1, order="F") for Xi in X])
+    Axb = At.T @ x - b
+    y1 = y - sigma * Axb
+    cy = c - At @ y1
+    by = float(b @ y1)
+    off2 = np.concatenate([[0], np.cumsum([n * n for n in ns])])
+    evs, dinfs, S = [], [], []
+    for i, n in enumerate(ns):
+        Si = cy[off2[i]:off2[i + 1]].reshape(n, n, order="F")
+        if i < nob:
+            z = np.sum(X[i] * Si, axis=0)
+            by += float(z.sum())
+            Si = Si - np.diag(z)
+        d = np.linalg.eigvalsh(Si)
+        S.append(Si)
+        evs.append(d)
+        dinfs.append(max(0.0, -d[0]) / (1 + abs(d[-1])))
+    obj = float(c @ x)
+    with _handle(At, b, c, K) as h:
+        h.set_dual(y, sigma)
+        h.mb_set_Y(Y)
+        k, dd, nneg = h.mb_kkt(update_dual=1)
+        y_dev, _ = h.get_dual()
+        for i, n in enumerate(ns):
+            vals, vecs = h.mb_block_eigs(i)
+            assert np.allclose(vals, evs[i], rtol=0, atol=1e-11 * max(1.0, np.abs(evs[i]).max()))
+            assert np.linalg.norm(S[i] @ vecs - vecs * vals) < 1e-10 * max(1.0, np.abs(evs[i]).max())
+            assert np.linalg.norm(vecs.T @ vecs - np.eye(n)) < 1e-12
+    assert abs(k.obj - obj) <= 1e-12 * max(1.0, abs(obj))
+    assert abs(k.pinf - np.linalg.norm(Axb) / (1 + np.linalg.norm(b))) <= 1e-12
+    assert abs(k.by - by) <= 1e-11 * max(1.0, abs(by))
+    assert abs(k.gap - abs(obj - by) / (abs(by) + abs(obj) + 1)) <= 1e-12
+    assert np.allclose(dd, dinfs, rtol=0, atol=1e-12)
+    assert abs(k.dinf - max(dinfs)) <= 1e-12
+    assert list(nneg) == [int(np.sum(d < 0)) for d in evs]
+    assert _rel(y_dev, y1) < 1e-13
+
+
+@pytest.mark.parametrize("line_search", [0, 1])
+def test_multiblock_update_matches_reference_rules(line_search):
+    """rank cut + escape of every block (ManiSDP_multiblock.m:114-153): widths, X_i = Y_i Y_i' of the new point (the
+    truncation basis is unique up to signs, X is not affected) and, with line_search = 1, the accepted step."""
+    from oracle.manisdp_ref import MultiblockProblem, _mb_line_search
+    from oracle.manopt_rtr import Cells
+    At, b, c, K = _instance(([8, 6, 7, 1, 5], 2, 5, 21))
+    ns, nob = K["s"], K["nob"]
+    rng = np.random.default_rng(8)
+    # block 0: numerically rank 2 of width 4 (cut expected); block 2: width 1; block 3: order 1 (< min_facsize)
+    p = [4, 3, 1, 1, 5]
+    Y = _point(ns, nob, p, rng)
+    Y[0][:, 2:] *= 1e-5
+    Y[0] /= np.linalg.norm(Y[0], axis=1, keepdims=True)
+    y = 0.2 * rng.standard_normal(At.shape[1])
+    sigma, theta, delta, alpha = 1.5, 1e-2, 3, 0.1
+    # the reference's rules on the host
+    X = [B @ B.T for B in Y]
+    x = np.concatenate([Xi.reshape(-1, order="F") for Xi in X])
+    y1 = y - sigma * (At.T @ x - b)
+    cy = c - At @ y1
+    off2 = np.concatenate([[0], np.cumsum([n * n for n in ns])])
+    Yn, Un, pn = [], [], []
+    for i, n in enumerate(ns):
+        Si = cy[off2[i]:off2[i + 1]].reshape(n, n, order="F")
+        if i < nob:
+            Si = Si - np.diag(np.sum(X[i] * Si, axis=0))
+        d, v = np.linalg.eigh(Si)
+        Yi, pi = Y[i], p[i]
+        if n < 2:
+            Yn.append(Yi); Un.append(np.zeros_like(Yi)); pn.append(pi)
+            continue
+        if pi > 1:
+            Us, e, _ = np.linalg.svd(Yi, full_matrices=False)
+            r = max(1, int(np.sum(e >= theta * e[0])))
+            if r < pi:
+                Yi, pi = Us[:, :r] * e[:r], r
+        nneg = int(np.sum(d < 0))
+        nne = max(min(nneg, delta), 1) if i < nob else min(nneg, delta)
+        if pi + nne > n:
+            nne = 0
+        V = v[:, :nne]
+        if line_search:
+            Un.append(np.hstack([np.zeros((n, pi)), V]))
+            Yi = np.hstack([Yi, np.zeros((n, nne))])
+        else:
+            Yi = np.hstack([Yi, alpha * V])
+            if i < nob:
+                Yi = Yi / np.linalg.norm(Yi, axis=1, keepdims=True)
+        Yn.append(Yi)
+        pn.append(pi + nne)
+    assert pn[0] < p[0] + delta  # the cut of block 0 happened
+    with _handle(At, b, c, K) as h:
+        h.set_dual(y, sigma)
+        h.mb_set_Y(Y)
+        h.mb_kkt(update_dual=1)
+        pd = h.mb_update(theta, delta, alpha, line_search=line_search, min_facsize=2)
+        assert pd == pn and h.mb_widths() == pn
+        Yd = h.mb_get_Y()
+        for i in range(len(ns)):
+            assert _rel(Yd[i] @ Yd[i].T, Yn[i] @ Yn[i].T) < 1e-10
+        if line_search:
+            Ud = h.mb_split(h.slot_get(7))
+            for i in range(len(ns)):
+                assert _rel(Ud[i] @ Ud[i].T, Un[i] @ Un[i].T) < 1e-10
+                assert _rel(Yd[i] @ Ud[i].T, Yn[i] @ Un[i].T) < 1e-10 or np.linalg.norm(Yn[i] @ Un[i].T) < 1e-14
+            sigma2 = 2 * sigma
+            h.set_sigma(sigma2)
+            a = h.line_search()
+            Yl = h.mb_get_Y()
+            ora = MultiblockProblem(At.tocsc(), b, c, ns, pn, nob, y1, sigma2)
+            ref = _mb_line_search(ora.co, Cells(Yn), Cells(Un), nob)
+            co_dev = ora.co(Cells(Yl))
+            co_ref = ora.co(ref)
+            assert abs(co_dev - co_ref) <= 1e-9 * max(1.0, abs(co_ref))
+            assert 0.8 ** 15 * 0.999 <= a <= 1.0
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("line_search", [0, 1])
+def test_multiblock_full_solve_matches_oracle(case, line_search):
+    """ManiSDP_multiblock end to end: same optimum as the oracle's restatement, all residues <= tol"""
+    from manisdp_matlab_b200 import ManiSDP_multiblock
+    from oracle.manisdp_ref import ManiSDP_multiblock as ref_mb
+    At, b, c, K = _instance(case)
+    opts = dict(tol=1e-8, AL_maxiter=400, line_search=line_search, verbose=False)
+    _, obj_ref, dref = ref_mb(At, b, c, K, opts)
+    assert dref["status"] == 0
+    X, obj, data = ManiSDP_multiblock(At, b, c, K, opts)
+    assert data["status"] == 0
+    assert max(data["gap"], data["pinf"], data["dinf"]) < 1e-8
+    assert abs(obj - obj_ref) <= 1e-6 * max(1.0, abs(obj_ref))
+    # feasibility of the returned blocks, evaluated on the host
+    x = np.concatenate([Xi.reshape(-1, order="F") for Xi in X])
+    assert np.linalg.norm(At.T @ x - b) / (1 + np.linalg.norm(b)) < 1e-7
+    for i in range(K["nob"]):
+        assert np.allclose(np.diag(X[i]), 1.0, atol=1e-12)
+
+
+def test_multiblock_equals_single_block_general_on_the_embedding():
+    """independent pin of the optimum: with K.nob = 0 the multi-block problem and its block-diagonal embedding into one
+    PSD cone (solved by the ManiSDP.m driver, pinned on SDPLIB) have the same optimal value"""
+    from instances import generators as G
+    from manisdp_matlab_b200 import ManiSDP, ManiSDP_multiblock
+    At, b, c, K = _instance(CASES[0])
+    _, obj_mb, d1 = ManiSDP_multiblock(At, b, c, K, dict(tol=1e-8, verbose=False))
+    Ab, cb, N, _ = G.embed_multiblock(At, c, K)
+    _, obj_g, d2 = ManiSDP(Ab, b, cb, {"s": N}, dict(tol=1e-8, verbose=False))
+    assert d1["status"] == 0 and d2["status"] == 0
+    assert abs(obj_mb - obj_g) <= 1e-6 * max(1.0, abs(obj_g))

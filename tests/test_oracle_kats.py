@@ -103,3 +103,24 @@ def test_product_laplacian_matches_oracle_and_reference_semantics():
     B = g.laplacian(4, ei, ej, w).toarray()
     assert np.array_equal(A, B)
     assert A[0, 1] == -7.0 and A[0, 0] == 1.0 + 5.0 + 7.0
+
+
+def test_multiblock_oracle_pinned_by_the_single_block_driver():
+    """ManiSDP_multiblock's restatement has no optimum of its own in the reference tree; it is pinned here through the
+    block-diagonal embedding: with K.nob = 0 the multi-block optimum equals the optimum of ONE PSD cone of order
+    sum(n_i) whose off-diagonal blocks are free, solved by the ManiSDP.m restatement (itself pinned on SDPLIB above)."""
+    from instances import generators as G
+    from oracle.manisdp_ref import ManiSDP, ManiSDP_multiblock
+    At, b, c, K = G.multiblock_random([6, 4, 5, 3], 0, 4, 1)
+    _, o1, d1 = ManiSDP_multiblock(At, b, c, K, dict(tol=1e-8))
+    Ab, cb, N, _ = G.embed_multiblock(At, c, K)
+    _, o2, d2 = ManiSDP(Ab, b, cb, {"s": N}, dict(tol=1e-8))
+    assert d1["status"] == 0 and d2["status"] == 0
+    assert abs(o1 - o2) <= 1e-7 * max(1.0, abs(o2))
+    # unit-diagonal blocks: feasibility and a dual certificate from the returned multipliers
+    At, b, c, K = G.multiblock_random([8, 6, 7], 3, 6, 3)
+    X, o3, d3 = ManiSDP_multiblock(At, b, c, K, dict(tol=1e-8))
+    assert d3["status"] == 0
+    for Xi in X:
+        assert np.allclose(np.diag(Xi), 1.0, atol=1e-12)
+    assert all(np.linalg.eigvalsh(S)[0] > -1e-6 for S in d3["S"])  # dual feasibility of the slack blocks

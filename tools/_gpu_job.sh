@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-MANISDP_EIG_DEBUG=1 timeout 300 python tools/run_configs.py theta112 2>&1 | grep -v "^{" | tail -3
-MANISDP_EIG_DEBUG=1 timeout 300 python tools/run_configs.py bqp60 2>&1 | tail -3 | cut -c1-400
+timeout 900 python -m pytest tests/test_gpu_multiblock.py -m gpu -q -x > gpurun_out/r2_pytest_mb.log 2>&1; tail -25 gpurun_out/r2_pytest_mb.log
+timeout 900 python -m pytest tests/test_gpu_affine.py tests/test_gpu_edges.py -m gpu -q -x > gpurun_out/r2_pytest_aff.log 2>&1; tail -5 gpurun_out/r2_pytest_aff.log
