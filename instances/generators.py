@@ -427,3 +427,140 @@ def embed_multiblock(At, c, K):
     c_big = np.zeros(N * N)
     c_big[mp] = c
     return At_big, c_big, N, roff
+
+
+def get_basis_on(n: int, d: int, var) -> np.ndarray:
+    """get_basis(n, d, var) of src/basicfunction/get_basis.m:1-33 with the optional variable list: the monomials of
+    degree <= d in the variables `var` (0-based, ascending), as exponent vectors over all n variables, in the order the
+    successor rule produces (the order of `get_basis` on len(var) variables)."""
+    var = [int(v) for v in var]
+    sub = get_basis(len(var), d)
+    out = np.zeros((n, sub.shape[1]), dtype=np.int64)
+    out[var, :] = sub
+    return out
+
+
+def bqpmom_sparse(n: int, I, coe: np.ndarray):
+    """Restates src/basicfunction/bqpmom_sparse.m:6-132: second-order moment relaxation of a BQP whose objective is a
+    sum of quadratics on the cliques I[0..t) (0-based variable lists, ascending), one PSD block per clique.
+    coe: coefficients of the non-constant multilinear monomials of degree <= 2 supported on a clique, in the
+    lexicographic (sortrows) order of their exponent vectors (example/example_bqp_sparse.m:9-17).
+    Returns (At, b, c, K) with At CSC (sum(mb^2) x ncons), K = {'s': [mb_1..mb_t]}; the caller sets K['nob']."""
+    t = len(I)
+    basis, mb, spl = [], [], []
+    for k in range(t):  # :10-28
+        bk = get_basis_on(n, 2, I[k])
+        bk = bk[:, (bk > 1).sum(axis=0) == 0]
+        basis.append(bk)
+        mb.append(bk.shape[1])
+        tmp = get_basis_on(n, 4, I[k])
+        keep = ((tmp > 2).sum(axis=0) == 0) & ((tmp % 2).sum(axis=0) != 0)
+        spl.append(tmp[:, keep])
+    spb = np.unique(np.concatenate(spl, axis=1).T, axis=0).T  # :29-30 unique + sortrows: lexicographic in x_1, x_2, ...
+    lsp = spb.shape[1]
+    where = _index_map(spb)
+    off = np.concatenate([[0], np.cumsum([v * v for v in mb])]).astype(np.int64)
+    mm = [[] for _ in range(lsp)]  # (i, j, k), i < j inside block k   :33-41
+    for k in range(t):
+        bt = basis[k].T
+        for i in range(mb[k]):
+            s = bt[i] + bt[i + 1:]
+            for o_, col in enumerate(s.tolist()):
+                mm[where[tuple(col)]].append((i, i + 1 + o_, k))
+    mc = [len(v) for v in I]
+    ncons = sum(v * (v + 1) // 2 for v in mb) - lsp + sum(a * (v - 1) for a, v in zip(mc, mb)) - sum(mb) + t  # :46
+    row, col, val = [0], [0], [1.0]  # :47-51
+    l = 1
+    for k in range(t):  # :52-65  diagonal of the degree-<=1 part equals X_1(1,1)
+        for i in range(1 if k == 0 else 0, mc[k] + 1):
+            row += [0, off[k] + i * mb[k] + i]
+            col += [l, l]
+            val += [0.5, -0.5]
+            l += 1
+    for k in range(t):  # :66-76  X_k(ij,ij) = X_k(i,i) = X_k(j,j)
+        pos = {v: a for a, v in enumerate(I[k])}
+        for i in range(mc[k] + 1, mb[k]):
+            v2 = np.nonzero(basis[k][:, i] == 1)[0]
+            c1, c2 = pos[int(v2[0])] + 1, pos[int(v2[1])] + 1
+            row += [off[k] + c1 * mb[k] + c1, off[k] + i * mb[k] + i, off[k] + c2 * mb[k] + c2, off[k] + i * mb[k] + i]
+            col += [l, l, l + 1, l + 1]
+            val += [0.5, -0.5, 0.5, -0.5]
+            l += 2
+    loa = []  # :77-84
+    for i in range(lsp):
+        a = []
+        for (p_, q_, k) in mm[i]:
+            a += [off[k] + q_ * mb[k] + p_, off[k] + p_ * mb[k] + q_]
+        loa.append(a)
+    for q in range(t):  # :85-104   x_k^2 * m_i = m_i
+        for k in range(mc[q]):
+            v = I[q][k]
+            for i in range(1, mb[q]):
+                if basis[q][v, i] == 0:
+                    bi = basis[q][:, i].copy()
+                    bi[v] = 2
+                    l1 = loa[where[tuple(bi.tolist())]]
+                    l2 = loa[where[tuple(basis[q][:, i].tolist())]]
+                    row += l1 + l2
+                    col += [l] * (len(l1) + len(l2))
+                    if len(l1) < len(l2):
+                        val += [1.0] * len(l1) + [-len(l1) / len(l2)] * len(l2)
+                    else:
+                        val += [len(l2) / len(l1)] * len(l1) + [-1.0] * len(l2)
+                    l += 1
+    for i in range(lsp):  # :106-116
+        idx = int(np.argmax([p_ for (p_, _, _) in mm[i]]))
+        for j in range(len(mm[i])):
+            if j != idx:
+                row += loa[i][2 * idx:2 * idx + 2] + loa[i][2 * j:2 * j + 2]
+                col += [l] * 4
+                val += [0.5, 0.5, -0.5, -0.5]
+                l += 1
+    assert l == ncons, (l, ncons)
+    At = sp.coo_matrix((val, (np.asarray(row, dtype=np.int64), col)), shape=(int(off[-1]), ncons)).tocsc()
+    At.sum_duplicates()
+    b = np.zeros(ncons)
+    b[0] = 1.0
+    nsp = spb[:, spb.sum(axis=0) <= 2]  # :119-125
+    nsp = nsp[:, (nsp > 1).sum(axis=0) == 0]
+    assert nsp.shape[1] == len(coe), (nsp.shape, len(coe))
+    c = np.zeros(int(off[-1]))
+    for i in range(nsp.shape[1]):  # :126-130
+        a = loa[where[tuple(nsp[:, i].tolist())]]
+        c[a] = coe[i] / len(a)
+    return At, b, c, {"s": [int(v) for v in mb]}
+
+
+def bqp_sparse_instance(t: int, q: int, seed: int):
+    """The clique structure of example/example_bqp_sparse.m:4-17 (t cliques of q variables, consecutive cliques share two)
+    with N(0,1) coefficients from NumPy's generator.  Returns (At, b, c, K, n, I, coe) with K['nob'] = t."""
+    n = q + (q - 2) * (t - 1)
+    I = [list(range((q - 2) * i, (q - 2) * (i + 1) + 2)) for i in range(t)]
+    mono = set()
+    for Ik in I:
+        bk = get_basis_on(n, 2, Ik)
+        bk = bk[:, (bk > 1).sum(axis=0) == 0]
+        mono.update(tuple(cl) for cl in bk.T.tolist())
+    coe = np.random.default_rng(seed).standard_normal(len(mono) - 1)
+    At, b, c, K = bqpmom_sparse(n, I, coe)
+    K["nob"] = t
+    return At, b, c, K, n, I, coe
+
+
+def bqp_sparse_bruteforce(n: int, I, coe: np.ndarray) -> float:
+    """min over x in {-1,+1}^n of the clique-sparse quadratic whose coefficients `coe` follow the monomial order of
+    bqpmom_sparse (lexicographic exponent vectors of the non-constant multilinear monomials of degree <= 2)."""
+    mono = set()
+    for Ik in I:
+        bk = get_basis_on(n, 2, Ik)
+        bk = bk[:, (bk > 1).sum(axis=0) == 0]
+        mono.update(tuple(cl) for cl in bk.T.tolist())
+    mono.discard(tuple([0] * n))
+    mono = sorted(mono)
+    E = np.array(mono, dtype=np.int64)  # (nmono, n)
+    best = np.inf
+    for bits in range(1 << n):
+        x = np.array([1.0 if (bits >> v) & 1 else -1.0 for v in range(n)])
+        vals = np.prod(np.where(E == 1, x[None, :], 1.0), axis=1)
+        best = min(best, float(coe @ vals))
+    return best

@@ -143,6 +143,16 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         pb.c_nnz = (int64_t)mxGetNumberOfElements(cc);
       }
     }
+    std::vector<int64_t> blocks;
+    if (pb.kind == MANISDP_MULTIBLOCK) {  // manisdp_mex('create', 4, sum(K.s), At, b, c, K.s, K.nob)
+      if (nrhs < 8) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "multi-block create needs K.s and K.nob");
+      const size_t t = mxGetNumberOfElements(prhs[6]);
+      blocks.resize(t);
+      for (size_t i = 0; i < t; ++i) blocks[i] = (int64_t)mxGetPr(prhs[6])[i];
+      pb.nblocks = (int32_t)t;
+      pb.nob = (int32_t)mxGetScalar(prhs[7]);
+      pb.block_sizes = blocks.data();
+    }
     manisdp_t* h = nullptr;
     manisdp_group_t* grp = nullptr;
     if (pb.kind == MANISDP_ONLYUNITDIAG && nrhs > 4 && mxGetNumberOfElements(prhs[4]) > 0) {
@@ -264,6 +274,68 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     CK(h, manisdp_hess(h), "hess");
     plhs[0] = mxCreateDoubleMatrix((mwSize)st.p, (mwSize)st.n, mxREAL);
     CK(h, manisdp_slot_get(h, MANISDP_SLOT_H, mxGetPr(plhs[0]), MANISDP_LAYOUT_ROWS), "slot_get");
+  } else if (c == "mb_set_Y") {
+    // Y: cell array, Y{i} is p_i x n_i (the layout of ManiSDP_multiblock.m; its memory image is n_i rows of p_i doubles)
+    const mxArray* Y = prhs[2];
+    if (!mxIsCell(Y)) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "mb_set_Y: Y must be a cell array");
+    const size_t t = mxGetNumberOfElements(Y);
+    std::vector<int64_t> p(t);
+    std::vector<double> cat;
+    for (size_t i = 0; i < t; ++i) {
+      const mxArray* Yi = mxGetCell(Y, i);
+      p[i] = (int64_t)mxGetM(Yi);
+      cat.insert(cat.end(), mxGetPr(Yi), mxGetPr(Yi) + mxGetNumberOfElements(Yi));
+    }
+    CK(h, manisdp_mb_set_Y(h, cat.data(), p.data()), "mb_set_Y");
+  } else if (c == "mb_get_Y" || c == "mb_widths") {
+    // sizes: prhs[2] = K.s
+    const size_t t = mxGetNumberOfElements(prhs[2]);
+    std::vector<int64_t> p(t);
+    CK(h, manisdp_mb_get_widths(h, p.data()), "mb_get_widths");
+    if (c == "mb_widths") {
+      plhs[0] = mxCreateDoubleMatrix((mwSize)t, 1, mxREAL);
+      for (size_t i = 0; i < t; ++i) mxGetPr(plhs[0])[i] = (double)p[i];
+    } else {
+      size_t total = 0;
+      for (size_t i = 0; i < t; ++i) total += (size_t)p[i] * (size_t)mxGetPr(prhs[2])[i];
+      std::vector<double> cat(total);
+      CK(h, manisdp_mb_get_Y(h, cat.data()), "mb_get_Y");
+      plhs[0] = mxCreateCellMatrix((mwSize)t, 1);
+      size_t o = 0;
+      for (size_t i = 0; i < t; ++i) {
+        const size_t ni = (size_t)mxGetPr(prhs[2])[i];
+        mxArray* Yi = mxCreateDoubleMatrix((mwSize)p[i], (mwSize)ni, mxREAL);
+        memcpy(mxGetPr(Yi), cat.data() + o, (size_t)p[i] * ni * sizeof(double));
+        o += (size_t)p[i] * ni;
+        mxSetCell(plhs[0], (mwIndex)i, Yi);
+      }
+    }
+  } else if (c == "mb_rand_Y") {
+    const size_t t = mxGetNumberOfElements(prhs[2]);
+    std::vector<int64_t> p(t);
+    for (size_t i = 0; i < t; ++i) p[i] = (int64_t)mxGetPr(prhs[2])[i];
+    CK(h, manisdp_mb_rand_Y(h, p.data(), (uint64_t)mxGetScalar(prhs[3])), "mb_rand_Y");
+  } else if (c == "mb_kkt") {
+    // [k, dinfs] = manisdp_mex('mb_kkt', h, update_dual, K.s)
+    const size_t t = mxGetNumberOfElements(prhs[3]);
+    manisdp_kkt_info k;
+    mxArray* d = mxCreateDoubleMatrix((mwSize)t, 1, mxREAL);
+    CK(h, manisdp_mb_kkt(h, (int32_t)mxGetScalar(prhs[2]), &k, mxGetPr(d), nullptr), "mb_kkt");
+    const char* names[] = {"obj", "by", "pinf", "dinf", "gap", "lam_min", "lam_max", "z_sum", "nneg"};
+    const double vals[] = {k.obj, k.by, k.pinf, k.dinf, k.gap, k.lam_min, k.lam_max, k.z_sum, (double)k.nneg};
+    plhs[0] = scalar_struct(names, vals, 9);
+    if (nlhs > 1)
+      plhs[1] = d;
+    else
+      mxDestroyArray(d);
+  } else if (c == "mb_update") {
+    // p = manisdp_mex('mb_update', h, theta, delta, alpha, line_search, min_facsize, K.s)
+    const size_t t = mxGetNumberOfElements(prhs[7]);
+    std::vector<int64_t> p(t);
+    CK(h, manisdp_mb_update(h, mxGetScalar(prhs[2]), (int32_t)mxGetScalar(prhs[3]), mxGetScalar(prhs[4]),
+                            (int32_t)mxGetScalar(prhs[5]), (int32_t)mxGetScalar(prhs[6]), p.data()), "mb_update");
+    plhs[0] = mxCreateDoubleMatrix((mwSize)t, 1, mxREAL);
+    for (size_t i = 0; i < t; ++i) mxGetPr(plhs[0])[i] = (double)p[i];
   } else if (c == "stats") {
     CK(h, manisdp_get_stats(h, &st), "get_stats");
     const char* names[] = {"n", "m", "p", "nnzC", "nnzA", "s_mode", "a_mode", "hv_total", "launches_total",

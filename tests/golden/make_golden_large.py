@@ -5,7 +5,9 @@
     is recorded so that the GPU test proves it solved the same instance.  Options of example/example_qsphere.m:21-27.
   * config 2: BQP q = 60 (n = 1831, m = 1 155 281), data/bqp_{Q,e}_60_1.txt, options of example/example_bqp.m:31-41.
 
-    python tests/golden/make_golden_large.py [qs60] [bqp60]
+    python tests/golden/make_golden_large.py [qs60] [bqp60] [bqpsparse]
+
+  * multi-block: the sparse BQP of example/example_bqp_sparse.m (20 blocks of order 211) through ManiSDP_multiblock.
 
 Results are merged into tests/golden/oracle_outputs_large.json.
 """
@@ -64,7 +66,21 @@ def bqp60():
                                oracle_seconds=time.perf_counter() - t0))
 
 
+def bqpsparse():
+    """multi-block: example/example_bqp_sparse.m:4-29 at its stated size (t = 20 cliques of q = 20 variables), N(0,1)
+    coefficients of numpy's default_rng(1) in place of MATLAB's rng(1) stream"""
+    At, b, c, K, n, I, coe = g.bqp_sparse_instance(20, 20, 1)
+    opts = dict(tol=1e-8, line_search=1, tau1=1)
+    t0 = time.perf_counter()
+    X, obj, data = ref.ManiSDP_multiblock(At, b, c, K, dict(opts, seed=0))
+    merge("bqp_sparse_20_20", dict(options=opts, status=int(data["status"]), obj=obj,
+                                   eta=max(data["gap"], data["pinf"], data["dinf"]), hv=data["hv_count"],
+                                   iters=data["iters"], blocks=len(K["s"]), block_order=int(K["s"][0]), m=int(At.shape[1]),
+                                   nnz=int(At.nnz), coe_sha256=hashlib.sha256(coe.tobytes()).hexdigest(),
+                                   oracle_seconds=time.perf_counter() - t0))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["qs60", "bqp60"]
+    which = sys.argv[1:] or ["qs60", "bqp60", "bqpsparse"]
     for w in which:
-        {"qs60": qs60, "bqp60": bqp60}[w]()
+        {"qs60": qs60, "bqp60": bqp60, "bqpsparse": bqpsparse}[w]()

@@ -19,6 +19,10 @@ bool mxIsSparse(const mxArray*);
 bool mxIsDouble(const mxArray*);
 bool mxIsStruct(const mxArray*);
 bool mxIsUint64(const mxArray*);
+bool mxIsCell(const mxArray*);
+mxArray* mxCreateCellMatrix(mwSize, mwSize);
+mxArray* mxGetCell(const mxArray*, mwIndex);
+void mxSetCell(mxArray*, mwIndex, mxArray*);
 int mxGetString(const mxArray*, char*, mwSize);
 double mxGetScalar(const mxArray*);
 double* mxGetPr(const mxArray*);

@@ -17,7 +17,7 @@
 #include "mex.h"
 
 struct mxArray_tag {
-  enum Kind { DENSE, SPARSE, CHARS, STRUCT, UINT64 } kind = DENSE;
+  enum Kind { DENSE, SPARSE, CHARS, STRUCT, UINT64, CELL } kind = DENSE;  // CELL: `fields` holds the elements
   size_t m = 0, n = 0;
   std::vector<double> pr;
   std::vector<mwIndex> ir, jc;
@@ -44,6 +44,20 @@ bool mxIsSparse(const mxArray* a) { return a && a->kind == mxArray::SPARSE; }
 bool mxIsDouble(const mxArray* a) { return a && (a->kind == mxArray::DENSE || a->kind == mxArray::SPARSE); }
 bool mxIsStruct(const mxArray* a) { return a && a->kind == mxArray::STRUCT; }
 bool mxIsUint64(const mxArray* a) { return a && a->kind == mxArray::UINT64; }
+bool mxIsCell(const mxArray* a) { return a && a->kind == mxArray::CELL; }
+mxArray* mxCreateCellMatrix(mwSize m, mwSize n) {
+  mxArray* a = new mxArray;
+  a->kind = mxArray::CELL;
+  a->m = m;
+  a->n = n;
+  a->fields.assign(m * n, nullptr);
+  return a;
+}
+mxArray* mxGetCell(const mxArray* a, mwIndex i) { return a->fields.at((size_t)i); }
+void mxSetCell(mxArray* a, mwIndex i, mxArray* v) {
+  delete a->fields.at((size_t)i);
+  a->fields[(size_t)i] = v;
+}
 int mxGetString(const mxArray* a, char* buf, mwSize len) {
   if (!mxIsChar(a) || len == 0) return 1;
   strncpy(buf, a->str.c_str(), len - 1);
@@ -151,6 +165,9 @@ mxArray* stub_struct(int nf, const char** names, const double* vals) {
   for (int i = 0; i < nf; ++i) mxSetFieldByNumber(a, 0, i, mxCreateDoubleScalar(vals[i]));
   return a;
 }
+mxArray* stub_cell(size_t n) { return mxCreateCellMatrix(n, 1); }
+void stub_cell_set(mxArray* a, size_t i, mxArray* v) { mxSetCell(a, i, v); }  // the cell takes ownership of v
+const mxArray* stub_cell_get(const mxArray* a, size_t i) { return mxGetCell(a, i); }
 void stub_free(mxArray* a) { delete a; }
 size_t stub_rows(const mxArray* a) { return a->m; }
 size_t stub_cols(const mxArray* a) { return a->n; }

@@ -297,3 +297,34 @@ def test_multiblock_equals_single_block_general_on_the_embedding():
     _, obj_g, d2 = ManiSDP(Ab, b, cb, {"s": N}, dict(tol=1e-8, verbose=False))
     assert d1["status"] == 0 and d2["status"] == 0
     assert abs(obj_mb - obj_g) <= 1e-6 * max(1.0, abs(obj_g))
+
+
+# ---- the reference's own multi-block example family: sparse BQP moment relaxations (example/example_bqp_sparse.m) -------
+@pytest.mark.parametrize("t,q,seed", [(3, 4, 1), (3, 5, 2), (4, 4, 3)])
+def test_sparse_bqp_relaxation_is_tight_on_small_instances(t, q, seed):
+    """oracle-free pin: bqpmom_sparse + ManiSDP_multiblock (all blocks unit-diagonal, options of
+    example_bqp_sparse.m:25-29) reach the exhaustive minimum of the clique-sparse BQP over {-1,+1}^n"""
+    from instances import generators as G
+    from manisdp_matlab_b200 import ManiSDP_multiblock
+    At, b, c, K, n, I, coe = G.bqp_sparse_instance(t, q, seed)
+    X, obj, data = ManiSDP_multiblock(At, b, c, K, dict(tol=1e-8, line_search=1, tau1=1, verbose=False))
+    assert data["status"] == 0 and max(data["gap"], data["pinf"], data["dinf"]) < 1e-8
+    assert abs(obj - G.bqp_sparse_bruteforce(n, I, coe)) <= 1e-6 * max(1.0, abs(obj))
+    for Xi in X:
+        assert np.allclose(np.diag(Xi), 1.0, atol=1e-12)
+
+
+def test_sparse_bqp_example_at_its_stated_size():
+    """example/example_bqp_sparse.m:4-29 at t = 20 cliques of q = 20 variables (20 blocks of order 211, m = 327 315,
+    nnz(At) = 1.4 M): optimum pinned by the oracle (tests/golden/make_golden_large.py bqpsparse), residues <= 1e-8"""
+    import json
+    import os
+    from instances import generators as G
+    from manisdp_matlab_b200 import ManiSDP_multiblock
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                       "oracle_outputs_large.json")))["bqp_sparse_20_20"]
+    At, b, c, K, n, I, coe = G.bqp_sparse_instance(20, 20, 1)
+    assert (At.shape[1], At.nnz, K["s"][0]) == (gold["m"], gold["nnz"], 211)
+    X, obj, data = ManiSDP_multiblock(At, b, c, K, dict(tol=1e-8, line_search=1, tau1=1, verbose=False))
+    assert data["status"] == 0 and max(data["gap"], data["pinf"], data["dinf"]) < 1e-8
+    assert abs(obj - gold["obj"]) <= 1e-6 * abs(gold["obj"])

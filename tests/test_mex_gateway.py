@@ -28,7 +28,8 @@ def test_matlab_drivers_keep_reference_signatures():
     sigs = {"ManiSDP_onlyunitdiag.m": "function [X, obj, data] = ManiSDP_onlyunitdiag(C, options)",
             "ManiSDP_unitdiag.m": "function [X, obj, data] = ManiSDP_unitdiag(At, b, c, K, options)",
             "ManiSDP_unittrace.m": "function [X, obj, data] = ManiSDP_unittrace(At, b, c, K, options)",
-            "ManiSDP.m": "function [X, obj, data] = ManiSDP(At, b, c, K, options)"}
+            "ManiSDP.m": "function [X, obj, data] = ManiSDP(At, b, c, K, options)",
+            "ManiSDP_multiblock.m": "function [X, obj, data] = ManiSDP_multiblock(At, b, c, K, options)"}
     for f, s in sigs.items():
         assert open(os.path.join(ROOT, "matlab", f)).readline().strip() == s
 
@@ -69,12 +70,22 @@ class Mex:
         L.stub_u64.argtypes = [vp]
         L.stub_field.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
         L.stub_call.argtypes = [C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_char_p, C.c_char_p, C.c_size_t]
+        L.stub_cell.restype = vp
+        L.stub_cell.argtypes = [C.c_size_t]
+        L.stub_cell_set.argtypes = [vp, C.c_size_t, vp]
+        L.stub_cell_get.restype = vp
+        L.stub_cell_get.argtypes = [vp, C.c_size_t]
 
     def arr(self, x):
         import scipy.sparse as sp
         L = self.lib
         if isinstance(x, str):
             return L.stub_string(x.encode())
+        if isinstance(x, list):  # cell array (column) of matrices
+            cell = L.stub_cell(len(x))
+            for i, e in enumerate(x):
+                L.stub_cell_set(cell, i, self.arr(e))
+            return cell
         if isinstance(x, dict):
             names = (C.c_char_p * len(x))(*[k.encode() for k in x])
             vals = (C.c_double * len(x))(*[float(v) for v in x.values()])
@@ -111,6 +122,16 @@ class Mex:
     def mat(self, a):
         m, n = self.lib.stub_rows(a), self.lib.stub_cols(a)
         out = np.ctypeslib.as_array(self.lib.stub_data(a), shape=(n, m)).T.copy()  # column-major -> (m, n)
+        self.lib.stub_free(a)
+        return out
+
+    def cell(self, a, count):
+        """cell array of matrices -> list of (m, n) arrays"""
+        out = []
+        for i in range(count):
+            e = self.lib.stub_cell_get(a, i)
+            m, n = self.lib.stub_rows(e), self.lib.stub_cols(e)
+            out.append(np.ctypeslib.as_array(self.lib.stub_data(e), shape=(n, m)).T.copy())
         self.lib.stub_free(a)
         return out
 
@@ -171,5 +192,48 @@ def test_gateway_executes_the_hot_path_like_the_ctypes_binding():
     mex.call(0, "destroy", None, handle=hd)
     with pytest.raises(RuntimeError, match="stale handle"):
         mex.call(0, "cost", None, handle=hd)
+    mex.lib.stub_free(hd)
+    mex.lib.stub_run_at_exit()
+
+
+@pytest.mark.gpu
+def test_gateway_drives_a_multiblock_handle():
+    """GPU: the multi-block commands of the gateway (cell arrays of p_i x n_i factors, K.s / K.nob at create) give the
+    numbers of the ctypes binding: create -> mb_set_Y -> tr_solve -> mb_kkt -> mb_update -> mb_get_Y."""
+    from instances import generators as G
+    from manisdp_matlab_b200 import Handle
+    At, b, c, K = G.multiblock_random([8, 6, 7, 2], 2, 5, 4)
+    ns, nob = K["s"], K["nob"]
+    rng = np.random.default_rng(2)
+    Y0 = []
+    for i, n in enumerate(ns):
+        B = rng.standard_normal((n, 2))
+        if i < nob:
+            B /= np.linalg.norm(B, axis=1, keepdims=True)
+        Y0.append(B)
+    m = At.shape[1]
+    with Handle("multiblock", sum(ns), At=At, b=b, c=c, block_sizes=ns, nob=nob) as h:
+        h.set_dual(np.zeros(m), 0.1)
+        h.mb_set_Y(Y0)
+        info = h.tr_solve(maxiter=4, maxinner=20, tolgradnorm=1e-8, use_graph=1)
+        k, dinfs, _ = h.mb_kkt(1)
+        pn = h.mb_update(1e-2, 8, 0.1, 0, 2)
+        Yref = h.mb_get_Y()
+    mex = Mex()
+    nsd = np.asarray(ns, dtype=np.float64).reshape(1, -1)
+    (hd,) = mex.call(1, "create", 4.0, float(sum(ns)), At, b.reshape(-1, 1), c.reshape(-1, 1), nsd, float(nob))
+    mex.call(0, "set_dual", None, np.zeros((m, 1)), 0.1, handle=hd)
+    mex.call(0, "mb_set_Y", None, [B.T for B in Y0], handle=hd)  # Y{i} is p_i x n_i in the reference
+    (s,) = mex.call(1, "tr_solve", None, dict(maxiter=4, maxinner=20, tolgradnorm=1e-8, use_graph=1), handle=hd)
+    assert mex.field(s, "cost") == info.cost and mex.field(s, "hv_count") == info.hv_count
+    kk, dd = mex.call(2, "mb_kkt", None, 1.0, nsd, handle=hd)
+    assert mex.field(kk, "obj") == k.obj and mex.field(kk, "pinf") == k.pinf and mex.field(kk, "dinf") == k.dinf
+    assert np.array_equal(mex.mat(dd).ravel(), dinfs)
+    (pp,) = mex.call(1, "mb_update", None, 1e-2, 8.0, 0.1, 0.0, 2.0, nsd, handle=hd)
+    assert [int(v) for v in mex.mat(pp).ravel()] == pn
+    (Yc,) = mex.call(1, "mb_get_Y", None, nsd, handle=hd)
+    for Ym, Yr in zip(mex.cell(Yc, len(ns)), Yref):
+        assert np.array_equal(Ym.T, Yr)
+    mex.call(0, "destroy", None, handle=hd)
     mex.lib.stub_free(hd)
     mex.lib.stub_run_at_exit()

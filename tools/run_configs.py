@@ -70,6 +70,24 @@ def run(name, cpu):
         opts = dict(tol=1e-8, sigma0=1e5, sigma_max=1e8, line_search=1, TR_maxiter=10, TR_maxinner=100)
         call = lambda mod, o: mod.ManiSDP_unittrace(At, b, c, K, o)
         n, m = int(K["s"]), At.shape[1]
+    elif name.startswith("bqpsparse:"):  # multi-block: example/example_bqp_sparse.m (t cliques of q variables)
+        from instances import generators as gi
+        t_, q_ = (int(v) for v in name.split(":")[1].split("x"))
+        At, b, c, K, _, _, _ = gi.bqp_sparse_instance(t_, q_, 1)
+        opts = dict(tol=1e-8, line_search=1, tau1=1)
+        call = lambda mod, o: mod.ManiSDP_multiblock(At, b, c, K, o)
+        n, m = int(sum(K["s"])), At.shape[1]
+    elif name == "demo1":  # multi-block: data/test.m on data/SDP_demo_1.mat (89 blocks, K.nob = 0)
+        import scipy.sparse as sp_
+        d = np.load(os.path.join(GOLDEN, "sdp_demo_1.npz"))
+        At = sp_.csc_matrix((d["At_data"], d["At_indices"], d["At_indptr"]), shape=tuple(d["At_shape"]))
+        c = np.zeros(At.shape[0])
+        c[d["c_idx"]] = d["c_val"]
+        b, K = d["b"], {"s": [int(v) for v in d["ns"]], "nob": 0}
+        opts = dict(tol=1e-4, gama=2, alpha=0.1, sigma0=1e-2, TR_maxinner=50, TR_maxiter=50, theta=1e-3, delta=4,
+                    line_search=0, AL_maxiter=300)
+        call = lambda mod, o: mod.ManiSDP_multiblock(At, b, c, K, o)
+        n, m = int(sum(K["s"])), At.shape[1]
     else:
         raise SystemExit(f"unknown config {name}")
     t_gen = time.perf_counter() - t0
@@ -97,7 +115,8 @@ def run(name, cpu):
                status=data["status"], launches=int(data.get("launches", 0)), gen_seconds=t_gen,
                modes=[data.get("s_mode"), data.get("a_mode")], p_max=max(data["fac_size"]),
                kkt_seconds=data.get("kkt_seconds"), eig_iters=data.get("eig_iters_total"),
-               setup_seconds=data.get("setup_seconds"), fac_size=data["fac_size"], phase_seconds=data.get("phase_seconds"),
+               setup_seconds=data.get("setup_seconds"), fac_size=data["fac_size"] if np.ndim(data["fac_size"]) == 1 else [max(v) for v in data["fac_size"]],
+               phase_seconds=data.get("phase_seconds"),
                options={k: v for k, v in o.items() if k not in ("verbose", "nccl_id")}, n_gpus=world)
     if world > 1 and int(os.environ["RANK"]) != 0:
         return
