@@ -50,8 +50,9 @@ enum {
   MANISDP_UNITDIAG = 1,     /* src/primal/ManiSDP_unitdiag.m     : oblique rows + AL on A(X) = b   */
   MANISDP_UNITTRACE = 2,    /* src/primal/ManiSDP_unittrace.m    : unit Frobenius sphere + AL      */
   MANISDP_GENERAL = 3,      /* src/primal/ManiSDP.m              : Euclidean + AL                  */
-  MANISDP_MULTIBLOCK = 4    /* src/primal/ManiSDP_multiblock.m   : product of oblique / Euclidean blocks + AL
+  MANISDP_MULTIBLOCK = 4,   /* src/primal/ManiSDP_multiblock.m   : product of oblique / Euclidean blocks + AL
                                (manifold ops: src/basicfunction/multiblockmanifold.m:1-42, src/C-files/ sources) */
+  MANISDP_DUAL_UNITDIAG = 5 /* src/dual/ManiDSDP_unitdiag.m      : Riemannian ADMM on the SOS (dual) form, oblique rows */
 };
 
 enum { MANISDP_LAYOUT_ROWS = 0, MANISDP_LAYOUT_COLS = 1 };
@@ -105,6 +106,15 @@ typedef struct {
    * (block, i, j) in 64-bit integer arithmetic at create time. */
   int32_t nblocks, nob;
   const int64_t *block_sizes;
+  /* MANISDP_DUAL_UNITDIAG only (ManiDSDP_unitdiag.m:8,35-44).  The caller's A (m x (K.f + n*n)) is passed split:
+   * At = A(:, K.f+1:end)' (n*n x m, CSC -- MATLAB builds it with one transpose), c = c(K.f+1:end), b = b;
+   * B = A(:, 1:K.f) (m x nfree, CSC) with its cost cf = c(1:K.f) when nfree = K.f > 0; dAAt = options.dAAt (m doubles)
+   * or NULL for diag(A*A') computed by the library (:40). */
+  const double *dAAt;
+  int64_t nfree;
+  const uint64_t *B_jc, *B_ir;
+  const double *B_pr;
+  const double *cf;
 } manisdp_problem;
 enum { MANISDP_SHARD_ROWS = 0, MANISDP_SHARD_COLS = 1 };
 
@@ -306,6 +316,15 @@ int manisdp_mb_get_block_eigs(manisdp_t *h, int32_t blk, double *vals, double *v
  * p_new (nblocks, may be NULL) receives the new widths. */
 int manisdp_mb_update(manisdp_t *h, double theta, int32_t delta, double alpha, int32_t line_search,
                       int32_t min_facsize, int64_t *p_new);
+
+/* ---- dual handles (kind MANISDP_DUAL_UNITDIAG; src/dual/ManiDSDP_unitdiag.m) ---------------------------------------
+ * The factor Y (n x p, unit rows) is the factor of the DUAL slack S = Y Y'; cost / grad / hess / tr_solve / line_search /
+ * rank_cut / escape work as on a UNITDIAG handle with the closures of ManiDSDP_unitdiag.m:171-191.  manisdp_kkt performs
+ * the ADMM step of :71-89 (y = D^-1 A (vec(S) - c), x <- x - sigma*As, w <- w - sigma*Af) and the eigen step on the primal
+ * matrix X = mat(x + bA) - diag(z); manisdp_get_dual returns that y, manisdp_set_dual / manisdp_set_sigma only change sigma.
+ * The ADMM multipliers: x (n*n, column-major vec of the n x n matrix) and w (nfree). */
+int manisdp_dual_get_state(manisdp_t *h, double *x, double *w);       /* either may be NULL */
+int manisdp_dual_set_state(manisdp_t *h, const double *x, const double *w);
 
 #ifdef __cplusplus
 }

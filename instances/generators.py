@@ -564,3 +564,42 @@ def bqp_sparse_bruteforce(n: int, I, coe: np.ndarray) -> float:
         vals = np.prod(np.where(E == 1, x[None, :], 1.0), axis=1)
         best = min(best, float(coe @ vals))
     return best
+
+
+# --------------------------------------------------------------------------------------------
+# SOS (dual) form of the BQP relaxation, input of ManiDSDP_unitdiag
+# --------------------------------------------------------------------------------------------
+def bqpsos(Q: np.ndarray, e: np.ndarray, n: int):
+    """Restates src/basicfunction/bqpsos.m:7-39: second-order SOS relaxation of min x'Qx + e'x, x_i^2 = 1.
+    Returns (A, b, dAAt, mb): A CSR (lsp x mb^2) whose rows partition the positions of the mb x mb Gram matrix by the
+    multilinear monomial they represent (x_i^2 = 1 reduces exponents mod 2), b the coefficient of each monomial,
+    dAAt = diag(A*A') = the number of positions of each monomial."""
+    spb = get_basis(n, 4)
+    spb = spb[:, (spb > 1).sum(axis=0) == 0]  # :8-11 multilinear monomials of degree <= 4
+    mb = comb(n + 2, 2) - n  # :12
+    lsp = spb.shape[1]
+    where = _index_map(spb)
+    rows = np.zeros(mb * mb, dtype=np.int64)
+    cols = np.zeros(mb * mb, dtype=np.int64)
+    dAAt = np.zeros(lsp)
+    dAAt[0] = mb
+    cols[:mb] = np.arange(mb) * mb + np.arange(mb)  # :18 the diagonal represents the constant monomial
+    ind = mb
+    bt = spb[:, :mb].T
+    for i in range(mb):  # :20-31
+        s = (bt[i] + bt[i + 1:]) % 2
+        for o_, colv in enumerate(s.tolist()):
+            j = i + 1 + o_
+            locb = where[tuple(colv)]
+            rows[ind] = rows[ind + 1] = locb
+            cols[ind] = i * mb + j
+            cols[ind + 1] = j * mb + i
+            dAAt[locb] += 2
+            ind += 2
+    A = sp.csr_matrix((np.ones(mb * mb), (rows, cols)), shape=(lsp, mb * mb))
+    b = np.zeros(lsp)  # :34-37
+    b[0] = np.trace(Q)
+    b[1:n + 1] = e
+    iu = np.triu(np.ones((n, n)), 1) != 0
+    b[n + 1:(n + 1) * (n + 2) // 2 - n] = 2 * Q.T[iu.T]  # MATLAB's column-major logical indexing of triu(.,1)
+    return A, b, dAAt, mb

@@ -14,11 +14,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmanisdp_b200.so")
 
-ONLYUNITDIAG, UNITDIAG, UNITTRACE, GENERAL, MULTIBLOCK = 0, 1, 2, 3, 4
+ONLYUNITDIAG, UNITDIAG, UNITTRACE, GENERAL, MULTIBLOCK, DUAL_UNITDIAG = 0, 1, 2, 3, 4, 5
 LAYOUT_ROWS, LAYOUT_COLS = 0, 1
 SLOT_Y, SLOT_YPROP, SLOT_G, SLOT_ETA, SLOT_R, SLOT_D, SLOT_HD, SLOT_U, SLOT_H = range(9)
 KIND_NAMES = {"onlyunitdiag": ONLYUNITDIAG, "unitdiag": UNITDIAG, "unittrace": UNITTRACE, "general": GENERAL,
-              "multiblock": MULTIBLOCK}
+              "multiblock": MULTIBLOCK, "dual_unitdiag": DUAL_UNITDIAG}
 
 _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
@@ -31,7 +31,9 @@ class Problem(C.Structure):
                 ("b", _f64p), ("c_ir", _u64p), ("c_pr", _f64p), ("c_nnz", C.c_int64),
                 ("rank", C.c_int32), ("world", C.c_int32), ("row_begin", C.c_int64), ("row_end", C.c_int64),
                 ("nccl_unique_id", C.c_void_p), ("force_mode", C.c_int32), ("shard_layout", C.c_int32),
-                ("nblocks", C.c_int32), ("nob", C.c_int32), ("block_sizes", C.POINTER(C.c_int64))]
+                ("nblocks", C.c_int32), ("nob", C.c_int32), ("block_sizes", C.POINTER(C.c_int64)),
+                ("dAAt", _f64p), ("nfree", C.c_int64), ("B_jc", _u64p), ("B_ir", _u64p), ("B_pr", _f64p),
+                ("cf", _f64p)]
 
 
 class TrOptions(C.Structure):
@@ -118,6 +120,8 @@ SIGNATURES = {
     "manisdp_group_line_search": (C.c_int, [_H, _f64p]),
     "manisdp_get_index_split": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,
                                           C.POINTER(C.c_int64)]),
+    "manisdp_dual_get_state": (C.c_int, [_H, _f64p, _f64p]),
+    "manisdp_dual_set_state": (C.c_int, [_H, _f64p, _f64p]),
     "manisdp_mb_set_Y": (C.c_int, [_H, _f64p, C.POINTER(C.c_int64)]),
     "manisdp_mb_get_Y": (C.c_int, [_H, _f64p]),
     "manisdp_mb_get_widths": (C.c_int, [_H, C.POINTER(C.c_int64)]),
@@ -173,7 +177,8 @@ class Handle:
     """Thin object wrapper over manisdp_t*; every method maps 1:1 onto a C-ABI call."""
 
     def __init__(self, kind, n, *, C_csc=None, At=None, b=None, c=None, device=0, rank=0, world=1,
-                 row_begin=0, row_end=None, nccl_id=None, force_mode=0, layout="rows", block_sizes=None, nob=0):
+                 row_begin=0, row_end=None, nccl_id=None, force_mode=0, layout="rows", block_sizes=None, nob=0,
+                 dAAt=None, B=None, cf=None):
         import scipy.sparse as sp
 
         self.lib = load()
@@ -220,6 +225,22 @@ class Handle:
                 cpr = _as_f64(np.asarray(c).ravel())
                 keep += [cpr]
                 pb.c_ir, pb.c_pr, pb.c_nnz = None, _pf(cpr), len(cpr)
+        self.nfree = 0
+        if pb.kind == DUAL_UNITDIAG:  # ManiDSDP_unitdiag.m:35-44: free part B (m x K.f), its cost cf, options.dAAt
+            if dAAt is not None:
+                dd = _as_f64(np.asarray(dAAt).ravel())
+                assert dd.shape == (pb.m,)
+                keep.append(dd)
+                pb.dAAt = _pf(dd)
+            if B is not None and B.shape[1] > 0:
+                Bm = sp.csc_matrix(B)
+                Bm.sort_indices()
+                bjc, bir, bpr = _as_u64(Bm.indptr), _as_u64(Bm.indices), _as_f64(Bm.data)
+                cff = _as_f64(np.asarray(cf).ravel())
+                assert Bm.shape == (pb.m, len(cff))
+                keep += [bjc, bir, bpr, cff]
+                pb.nfree, pb.B_jc, pb.B_ir, pb.B_pr, pb.cf = Bm.shape[1], _pu(bjc), _pu(bir), _pf(bpr), _pf(cff)
+                self.nfree = Bm.shape[1]
         if nccl_id is not None:
             idbuf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
             keep.append(idbuf)
@@ -411,6 +432,19 @@ class Handle:
         s = Stats()
         self._ck(self.lib.manisdp_get_stats(self._h, C.byref(s)), "get_stats")
         return s
+
+    # -- dual handles: the ADMM multipliers x (n x n) and w (K.f)
+    def dual_state(self):
+        x = np.empty(self.n * self.n)
+        w = np.empty(max(1, self.nfree))
+        self._ck(self.lib.manisdp_dual_get_state(self._h, _pf(x), _pf(w)), "dual_get_state")
+        return x, w[:self.nfree]
+
+    def dual_set_state(self, x=None, w=None):
+        xx = None if x is None else _as_f64(np.asarray(x).ravel())
+        ww = None if w is None or self.nfree == 0 else _as_f64(np.asarray(w).ravel())
+        self._ck(self.lib.manisdp_dual_set_state(self._h, None if xx is None else _pf(xx),
+                                                 None if ww is None else _pf(ww)), "dual_set_state")
 
     # -- multi-block handles (manisdp_mb_*): a point is a list of (n_i, p_i) arrays, one row per vertex of the block
     def _i64(self, v):

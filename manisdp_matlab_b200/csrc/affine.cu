@@ -28,6 +28,10 @@
 #define T_S 4      // sphere scalars
 #define T_AUX 5
 
+// penalty the closure kernels see: sigma of the primal AL drivers; -sigma on a dual (ManiDSDP) handle, whose cost is
+// <C_eff, S> + sigma/2 |S|^2 - sigma/2 |A~ vec(S) - A~ c|^2 + const (dual.cu)
+static inline double csig(const manisdp_handle* h) { return h->dual.on ? -h->sigma : h->sigma; }
+
 static int mgrid(const manisdp_handle* h, int64_t total, int per_block = MSDP_THREADS) {
   int64_t nb = (total + per_block - 1) / per_block;
   const int64_t cap = std::min<int64_t>((int64_t)h->num_sms * 8, MSDP_MAX_BLOCKS);
@@ -307,8 +311,9 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_rowlist_apply(RowlistArgs a, R
 }
 
 // cost scalars: f = <C,X> + sigma/2 |r|^2  (ManiSDP_unitdiag.m:156)
-__global__ void k_cost_finish(RtrState* st, double sigma, int mode, int w) {
-  const double f = st->tmp[T_CX] + 0.5 * sigma * st->tmp[T_RR];
+__global__ void k_cost_finish(RtrState* st, double sigma, int mode, int w, int dual) {
+  // dual handles: tmp[6] = sigma/2 |Z'Z|_F^2 + sigma/2 |Af|^2 + k0 (dual.cu: msdp_dual_cost_extra)
+  const double f = st->tmp[T_CX] + 0.5 * sigma * st->tmp[T_RR] + (dual ? st->tmp[6] : 0.0);
   st->tmp[T_F] = f;
   if (mode == CG_COSTONLY) return;
   st->cx[w] = st->tmp[T_CX];
@@ -765,7 +770,7 @@ static const int* accepted_flag(manisdp_handle* h) { return &h->st->accepted; }
 // w = A(P Q') into `out`; mode 1 turns it into the residual r and leaves |r|^2 in tmp[T_RR]
 static int apply_A(manisdp_handle* h, const double* P, const double* Q, double* out, int mode, int skip_if_stopped) {
   const int ld = (int)h->ld;
-  const double inv_sigma = 1.0 / h->sigma;
+  const double inv_sigma = h->dual.on ? 0.0 : 1.0 / h->sigma;  // dual handles: r = A~ vec(S) - A~ c, h->y is the ADMM's y
   if (h->a_mode == MODE_DENSE) {
     MSDP_TRY(msdp_gemm_nt(h, P, ld, Q, ld, (int)h->n, ld, h->Mbuf, 1.0, skip_if_stopped ? &h->st->stop : nullptr, 1));
     k_gather_spmv<<<mgrid(h, h->m), MSDP_THREADS, 0, h->stream>>>(h->Ad.kptr, h->Ad.klin, h->Ad.ka, h->Mbuf, h->m, out,
@@ -854,7 +859,8 @@ static int cost_at(manisdp_handle* h, const double* Z, double* resid_out, int mo
                                                                          h->n * h->ld / 2, T_CX, 0, nullptr);
     KERNEL_CHECK(h);
   }
-  k_cost_finish<<<1, 1, 0, h->stream>>>(h->st, h->sigma, mode, w);
+  if (h->dual.on) MSDP_TRY(msdp_dual_cost_extra(h, Z, resid_out, mode == CG_COSTONLY ? -1 : w));
+  k_cost_finish<<<1, 1, 0, h->stream>>>(h->st, csig(h), mode, w, h->dual.on);
   KERNEL_CHECK(h);
   return MANISDP_OK;
 }
@@ -865,11 +871,12 @@ static int grad_at(manisdp_handle* h, int w, int mode, const int* pred) {
   const int ld = (int)h->ld;
   const int64_t nvec = h->n * h->ld / 2;
   if (h->s_mode == MODE_DENSE) {
-    MSDP_TRY(form_eS(h, h->resid[w], h->sigma, pred));  // eS = C + sigma*At*Axb   (ManiSDP_unitdiag.m:160)
+    MSDP_TRY(form_eS(h, h->resid[w], csig(h), pred));  // eS = C + sigma*At*Axb   (ManiSDP_unitdiag.m:160)
     MSDP_TRY(msdp_gemm_nn(h, h->eS, (int)h->n, Z, ld, ld, G, ld, 2.0, 0.0, pred));  // eG = 2*Y*eS (:161)
   } else {
     MSDP_TRY(apply_S_sparse(h, Z, h->resid[w], 2.0 * h->sigma, nullptr, nullptr, 0.0, 2.0, G, 0.0, ld, pred, 0, true));
   }
+  if (h->dual.on) MSDP_TRY(msdp_dual_grad_extra(h, Z, G, w, pred));  // + 2*sigma*Y*(Y'Y): X = eS + sigma*S (ManiDSDP_unitdiag.m:181-182)
   if (h->mf == MF_SPHERE) {
     k_dot_guard<<<mgrid(h, nvec), MSDP_THREADS, 0, h->stream>>>(Z, G, h->st, h->partials, nvec, T_S, 0, pred);
     KERNEL_CHECK(h);
@@ -898,6 +905,7 @@ static int grad_at(manisdp_handle* h, int w, int mode, const int* pred) {
 // driver reads the state back once per TR iteration (rtr.cu) and graphs are built per value of pt.
 int msdp_affine_costgrad(manisdp_handle* h, int which, int cg_mode) {
   const int w = which >= 0 ? which : (which == -1 ? (h->pt ^ 1) : h->pt);
+  if (h->dual.on && h->dual.dirty) MSDP_TRY(msdp_dual_refresh(h));
   if (cg_mode == CG_TR_DEFER) return msdp_fail(h, MANISDP_E_ARG, "affine kinds are not row-sharded");
   MSDP_TRY(cost_at(h, h->Ybuf[w], h->resid[w], cg_mode, w));
   if (cg_mode == CG_COSTONLY) return MANISDP_OK;
@@ -912,7 +920,7 @@ int msdp_affine_hess(manisdp_handle* h, const double* D, double* Hout, int tail_
   const int ld = (int)h->ld;
   const int skip = (tail_mode != TAIL_NONE);
   const int64_t nvec = h->n * h->ld / 2;
-  const double s4 = 4.0 * h->sigma;
+  const double s4 = 4.0 * csig(h);
   // AyU-part: wU = A(U Y')  (ManiSDP_unitdiag.m:167-168 / ManiSDP.m:162-163)
   MSDP_TRY(apply_A(h, D, Y, h->wU, 0, skip));
   if (h->s_mode == MODE_DENSE) {
@@ -931,6 +939,8 @@ int msdp_affine_hess(manisdp_handle* h, const double* D, double* Hout, int tail_
     // 2*(C + sigma*At(r))*U + 4*sigma*At(wU)*Y in one rowlist pass
     MSDP_TRY(apply_S_sparse(h, D, h->resid[w], 2.0 * h->sigma, Y, h->wU, s4, 2.0, Hout, 0.0, ld, nullptr, skip, true));
   }
+  // dual handles: + 2*sigma*(Y*(Y'U + U'Y) + U*(Y'Y))   (ManiDSDP_unitdiag.m:189 with X = eS + sigma*S)
+  if (h->dual.on) MSDP_TRY(msdp_dual_hess_extra(h, Y, D, Hout, w, skip));
   if (h->mf == MF_SPHERE) {
     k_dot_guard<<<mgrid(h, nvec), MSDP_THREADS, 0, h->stream>>>(Hout, Y, h->st, h->partials, nvec, T_S, skip, nullptr);
     KERNEL_CHECK(h);
@@ -956,6 +966,7 @@ int msdp_affine_hess(manisdp_handle* h, const double* D, double* Hout, int tail_
 }
 
 int msdp_affine_cost_only(manisdp_handle* h, const double* Z, double* f_host) {
+  if (h->dual.on && h->dual.dirty) MSDP_TRY(msdp_dual_refresh(h));
   MSDP_TRY(cost_at(h, Z, h->wtmp, CG_COSTONLY, 0));
   const int keep = h->pt;
   MSDP_TRY(msdp_sync_state(h));
@@ -1019,6 +1030,23 @@ int msdp_affine_kkt(manisdp_handle* h, int update_dual, manisdp_kkt_info* out) {
   // y changed (or eS now holds the KKT slack): the closure caches of the point are stale
   h->cache_valid = 0;
   h->grad_valid = 0;
+  return MANISDP_OK;
+}
+
+// helpers shared with dual.cu: z_i = <Y_i, T_i> (+ sum into st->tmp[slot]); dst[touched] = base + coef * mat(At * vec)
+int msdp_affine_rowdot(manisdp_handle* h, const double* Y, const double* T, double* zout, int slot) {
+  const int ld = (int)h->ld;
+  DISPATCH_GEOM(row_geom(h->ld), {
+    k_rowdot<GS, VPL><<<rows_grid(h, h->n, GS), MSDP_THREADS, 0, h->stream>>>(Y, T, zout, h->st, h->partials, h->n, ld,
+                                                                             slot);
+  });
+  KERNEL_CHECK(h);
+  return MANISDP_OK;
+}
+int msdp_affine_touch(manisdp_handle* h, const double* vec, double coef, const double* base, double* dst) {
+  k_touch_update<<<mgrid(h, h->Ad.nu), MSDP_THREADS, 0, h->stream>>>(h->Ad.upos, h->Ad.lptr, h->Ad.lk, h->Ad.la, vec,
+                                                                    coef, base, dst, h->Ad.nu, nullptr, h->st, 0);
+  KERNEL_CHECK(h);
   return MANISDP_OK;
 }
 

@@ -361,7 +361,7 @@ static int upload_csr_from_csc(manisdp_handle* h, Csr& out, const uint64_t* jc, 
 
 static int create_impl(manisdp_handle* h, const manisdp_problem* pb) {
   NvtxRange nvtx_range("manisdp:create");
-  if (pb->kind < MANISDP_ONLYUNITDIAG || pb->kind > MANISDP_MULTIBLOCK) return msdp_fail(h, MANISDP_E_ARG, "bad kind");
+  if (pb->kind < MANISDP_ONLYUNITDIAG || pb->kind > MANISDP_DUAL_UNITDIAG) return msdp_fail(h, MANISDP_E_ARG, "bad kind");
   if (pb->n < 1) return msdp_fail(h, MANISDP_E_ARG, "n must be >= 1");
   h->kind = pb->kind;
   h->mf = (pb->kind == MANISDP_UNITTRACE) ? MF_SPHERE : (pb->kind == MANISDP_GENERAL ? MF_EUCLID : MF_OBLIQUE);
@@ -429,6 +429,44 @@ static int create_impl(manisdp_handle* h, const manisdp_problem* pb) {
       if (pb->world > 1) return msdp_fail(h, MANISDP_E_ARG, "multi-block handles are single-GPU (SURVEY 8e: small blocks, latency-bound)");
       MSDP_TRY(msdp_mb_setup(h, pb));
     }
+    if (h->kind == MANISDP_DUAL_UNITDIAG) {
+      // the engine sees A~ = D^-1/2 A, b_eff = A~ c and (rebuilt every ADMM step) C_eff = bA + x - sigma*c  (dual.cu)
+      if (!pb->At_jc || !pb->At_ir || !pb->At_pr || !pb->b || !pb->c_pr)
+        return msdp_fail(h, MANISDP_E_ARG, "dual handles need At, b and c");
+      const int64_t m = pb->m;
+      const uint64_t nz = pb->At_jc[m], nn = (uint64_t)pb->n * (uint64_t)pb->n;
+      std::vector<double> dAAt((size_t)m, 0.0), pr(pb->At_pr, pb->At_pr + nz), beff((size_t)m, 0.0), cd((size_t)nn, 0.0);
+      if (pb->c_ir) {
+        for (int64_t q = 0; q < pb->c_nnz; ++q) {
+          if (pb->c_ir[q] >= nn) return msdp_fail(h, MANISDP_E_ARG, "c: index out of range");
+          cd[(size_t)pb->c_ir[q]] += pb->c_pr[q];
+        }
+      } else {
+        if ((uint64_t)pb->c_nnz != nn) return msdp_fail(h, MANISDP_E_ARG, "dense c must have n*n entries");
+        std::copy(pb->c_pr, pb->c_pr + nn, cd.begin());
+      }
+      for (int64_t k = 0; k < m; ++k) {
+        double dk = 0.0;
+        for (uint64_t e = pb->At_jc[k]; e < pb->At_jc[k + 1]; ++e) dk += pb->At_pr[e] * pb->At_pr[e];
+        dAAt[(size_t)k] = pb->dAAt ? pb->dAAt[k] : dk;  // ManiDSDP_unitdiag.m:40
+        if (!(dAAt[(size_t)k] > 0.0)) return msdp_fail(h, MANISDP_E_ARG, "dual: diag(A*A') must be positive");
+        const double is = 1.0 / sqrt(dAAt[(size_t)k]);
+        double acc = 0.0;
+        for (uint64_t e = pb->At_jc[k]; e < pb->At_jc[k + 1]; ++e) {
+          if (pb->At_ir[e] >= nn) return msdp_fail(h, MANISDP_E_ARG, "At: row index out of range");
+          pr[(size_t)e] *= is;
+          acc += pr[(size_t)e] * cd[(size_t)pb->At_ir[e]];
+        }
+        beff[(size_t)k] = acc;
+      }
+      manisdp_problem q = *pb;
+      q.At_pr = pr.data();
+      q.b = beff.data();
+      q.force_mode = (pb->force_mode & ~2) | 1;  // dense S: C_eff is a dense n x n matrix
+      MSDP_TRY(msdp_affine_setup(h, &q));
+      MSDP_TRY(msdp_dual_setup(h, pb, dAAt));
+      return MANISDP_OK;
+    }
     MSDP_TRY(msdp_affine_setup(h, pb));
   }
   return MANISDP_OK;
@@ -444,6 +482,7 @@ static void free_all(manisdp_handle* h) {
   msdp_col_destroy(h);
   msdp_affine_free(h);
   msdp_mb_free(h);
+  msdp_dual_free(h);
   double* arrs[] = {h->Ybuf[0], h->Ybuf[1], h->Gbuf[0], h->Gbuf[1], h->eta[0], h->eta[1], h->r, h->d, h->Hd,
                     h->Uslot, h->Hslot, h->gatherbuf, h->eG[0], h->eG[1], h->zdiag, h->partials, h->C.val,
                     h->eigvecs};
@@ -561,8 +600,9 @@ int manisdp_set_dual(manisdp_t* h, const double* y, double sigma) {
   if (!h) return MANISDP_E_ARG;
   if (h->kind == MANISDP_ONLYUNITDIAG) return msdp_fail(h, MANISDP_E_ARG, "ONLYUNITDIAG has no dual vector");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  if (y) CUDA_TRY(h, cudaMemcpy(h->y, y, (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice));
+  if (y && !h->dual.on) CUDA_TRY(h, cudaMemcpy(h->y, y, (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice));
   if (sigma > 0) h->sigma = sigma;
+  if (h->dual.on) h->dual.dirty = 1;  // C_eff = bA + x - sigma*c and k0 depend on sigma (dual.cu)
   h->cache_valid = h->grad_valid = 0;
   return MANISDP_OK;
 }

@@ -40,6 +40,7 @@ struct RtrState {
   // multi-block handles (multiblockmanifold.m:1-42): rows [0, nob_rows) are unit vectors (oblique blocks), the rows behind
   // them are Euclidean.  Every other oblique handle keeps LLONG_MAX here (all rows oblique).
   long long nob_rows;
+  double dual_k0, dual_sigma;  // dual handles: constant of the cost and the ADMM penalty (read by the dual.cu kernels)
 };
 
 struct Csr {  // row lists on the device (int32 indices; n, nnz < 2^31)
@@ -79,6 +80,21 @@ struct ADense {
   int* lk = nullptr;        // nnz
   double* la = nullptr;
   int64_t nnz = 0, nu = 0;
+};
+
+// dual (ManiDSDP) handles, dual.cu
+struct DualData {
+  int on = 0, dirty = 0;
+  int64_t nfree = 0;
+  double *bA = nullptr, *cpsd = nullptr, *x = nullptr;  // n x n: (A' D^-1 b), PSD part of c, ADMM multiplier
+  double *isd = nullptr, *borig = nullptr;              // m: 1/sqrt(dAAt), the caller's b
+  double* gram[2] = {nullptr, nullptr};                 // ld x ld: Y'Y of point buffer w
+  double *gramS = nullptr, *gramW = nullptr, *gram_part = nullptr;  // scratch Gram (line search), Y'U, chunk partials
+  int gram_ld = 0;
+  size_t gram_part_cap = 0;
+  int *B_jc = nullptr, *B_ir = nullptr;                 // free part of A (m x nfree, CSC)
+  double *B_pr = nullptr, *cf = nullptr, *w = nullptr;  // its values, cost of the free variables, their multiplier
+  double normc = 1.0;
 };
 
 struct manisdp_handle {
@@ -204,6 +220,8 @@ struct manisdp_handle {
   int mb_have_eigs = 0;                  // mb_evals / mb_evecs belong to the current point
   std::vector<double> mb_evals;          // eigenvalues of every S{i} of the last mb_kkt, stacked by block (ascending)
   std::vector<double> mb_evecs;          // eigenvectors, block i at mb_off2[i], row-major n_i x n_i (column k = k-th vector)
+  DualData dual;
+  int rank_strict = 0;                   // rank estimate counts e > theta*e1 (ManiDSDP_unitdiag.m:91) instead of >=
   std::string err;
 };
 int msdp_scratch(manisdp_handle* h, int slot, size_t bytes, void** out);  // api.cu

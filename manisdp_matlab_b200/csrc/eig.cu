@@ -671,6 +671,8 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
     out->by = out->obj;
     out->pinf = 0.0;
     out->gap = 0.0;
+  } else if (h->dual.on) {
+    MSDP_TRY(msdp_dual_kkt(h, update_dual, out));  // ADMM step; the eigen step below works on X = eX - diag(z)
   } else {
     MSDP_TRY(msdp_affine_kkt(h, update_dual, out));
   }
@@ -736,7 +738,7 @@ int msdp_kkt(manisdp_handle* h, int delta, double eig_tol, int update_dual, mani
   }
   out->lam_min = vals.empty() ? 0.0 : vals[0];
   out->lam_max = lam_max;
-  out->dinf = std::max(0.0, -out->lam_min) / (1.0 + lam_max);  // ManiSDP_onlyunitdiag.m:51
+  out->dinf = std::max(0.0, -out->lam_min) / (1.0 + (h->dual.on ? fabs(lam_max) : lam_max));  // ManiSDP_onlyunitdiag.m:51 / ManiDSDP_unitdiag.m:87
   h->last_dinf = out->dinf;
   out->nneg = std::min(nneg, delta);
   out->eig_iters = iters;
@@ -846,7 +848,7 @@ int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, in
     const double s1t = sqrt(std::max(0.0, ev[p - 1]));
     int rt = 0;
     for (int i = 0; i < p; ++i)
-      if (sqrt(std::max(0.0, ev[i])) >= theta * s1t) ++rt;
+      if (h->rank_strict ? sqrt(std::max(0.0, ev[i])) > theta * s1t : sqrt(std::max(0.0, ev[i])) >= theta * s1t) ++rt;
     if (apply && rt <= p - 1 && rt >= 1 && !es.rank_have_Z) {
       std::vector<double> ev2;
       ScopedSeconds tz(g_rank_vecs_s);
@@ -861,7 +863,7 @@ int msdp_rank_cut(manisdp_handle* h, double theta, int apply, int64_t* r_out, in
   const double s1 = sqrt(std::max(0.0, ev[p - 1]));
   int r = 0;
   for (int i = 0; i < p; ++i)
-    if (sqrt(std::max(0.0, ev[i])) >= theta * s1) ++r;
+    if (h->rank_strict ? sqrt(std::max(0.0, ev[i])) > theta * s1 : sqrt(std::max(0.0, ev[i])) >= theta * s1) ++r;  // ManiDSDP_unitdiag.m:91 is strict
   if (r_out) *r_out = r;
   if (apply && r <= p - 1 && r >= 1) {
     ScopedSeconds ti(g_rank_install_s);

@@ -375,3 +375,114 @@ def ManiSDP_multiblock(At, b, c, K, options=None):
         _say(o, "Iteration maximum is reached!")
     _say(o, f"ManiSDP: optimum = {obj:0.8f}, time = {data['time']:0.2f}s")
     return X, obj, data
+
+
+# ManiDSDP_unitdiag.m:10-26
+DUAL_DEFAULTS = dict(p0=None, ADMM_maxiter=300, gama=2, sigma0=1e-3, sigma_min=1e-3, sigma_max=1e7, tol=1e-8, theta=1e-3,
+                     delta=8, alpha=0.1, tolgradnorm=1e-8, TR_maxinner=20, TR_maxiter=4, tau1=1e1, tau2=1e2,
+                     line_search=0)
+
+
+def ManiDSDP_unitdiag(A, b, c, K, options=None):
+    """sup <C,X> + <c_f,w> s.t. A(X) + B(w) = b, X >= 0, with a unit-diagonal dual slack -- the dual approach
+    (Riemannian ADMM) of src/dual/ManiDSDP_unitdiag.m:8.  A: (m, K.f + n*n), c: (K.f + n*n,), K = {'f': .., 's': n},
+    options['dAAt'] = diag(A*A') when known (bqpsos returns it)."""
+    import math
+
+    import scipy.sparse as sp
+
+    o = dict(DUAL_DEFAULTS)
+    o.update(options or {})
+    for k_, v_ in dict(seed=0, verbose=True, use_graph=1, device=0, eig_tol=0.0).items():
+        o.setdefault(k_, v_)
+    n = int(K["s"])
+    nf = int(K.get("f", 0))
+    A = sp.csc_matrix(A)
+    bd = np.asarray(b, dtype=np.float64).ravel()
+    cd = np.asarray(c.todense()).ravel() if sp.issparse(c) else np.asarray(c, dtype=np.float64).ravel()
+    m = A.shape[0]
+    _say(o, "ManiSDP is starting...")
+    _say(o, f"SDP size: n = {n}, m = {m}")
+    if o["p0"] is None:
+        o["p0"] = int(math.ceil(math.log(m)))  # :11
+    B, Ap = A[:, :nf], A[:, nf:]  # :34-37
+    cf, cp = cd[:nf], cd[nf:]
+    sigma, gama = float(o["sigma0"]), float(o["gama"])
+    data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[], seta=[], tr_seconds=0.0)
+    phase = dict(create=0.0, line_search=0.0, tr_solve=0.0, kkt=0.0, rank=0.0, escape=0.0)
+    t0 = time.perf_counter()
+    gap0 = pinf0 = dinf0 = None
+
+    def timed(name, fn, *a):
+        t1 = time.perf_counter()
+        r_ = fn(*a)
+        phase[name] += time.perf_counter() - t1
+        return r_
+
+    with _lib.Handle("dual_unitdiag", n, At=Ap.T.tocsc(), b=bd, c=cp, device=o["device"], dAAt=o.get("dAAt"), B=B,
+                     cf=cf, force_mode=int(o.get("force_mode", 0))) as h:
+        h.set_sigma(sigma)
+        _init_point(h, o)
+        phase["create"] = time.perf_counter() - t0
+        staged = False
+        for it in range(1, int(o["ADMM_maxiter"]) + 1):
+            data["fac_size"].append(h.p)
+            if staged:
+                timed("line_search", h.line_search)  # :66-68
+            info = timed("tr_solve", h.tr_solve, o["TR_maxiter"], o["TR_maxinner"], o["tolgradnorm"], o["use_graph"])
+            data["hv_count"] += info.hv_count
+            data["tr_iters"] += info.iters
+            data["tr_seconds"] += info.seconds
+            gradnorm = info.gradnorm
+            # ADMM step + residues + eig(X)  (:71-88)
+            k = timed("kkt", h.kkt, int(o["delta"]), o["eig_tol"] if o["eig_tol"] > 0 else -float(o["tol"]), 1)
+            obj, gap, pinf, dinf = k.obj, k.gap, k.pinf, k.dinf
+            data["eig_unconverged"] = data.get("eig_unconverged", 0) + (0 if k.eig_converged else 1)
+            p = h.p
+            r, _ = timed("rank", h.rank_cut, o["theta"], False)  # :89-91
+            _say(o, f"Iter {it}, obj:{obj:0.8f}, gap:{gap:0.1e}, pinf:{pinf:0.1e}, dinf:{dinf:0.1e}, "
+                    f"gradnorm:{gradnorm:0.1e}, r:{r}, p:{p}, sigma:{sigma:0.3f}, time:{time.perf_counter()-t0:0.2f}s")
+            eta = max(gap, pinf, dinf)
+            data["seta"].append(eta)
+            if eta < o["tol"]:
+                _say(o, "Optimality is reached!")
+                break
+            if it % 50 == 0:
+                if it > 100 and gap > gap0 and pinf > pinf0 and dinf > dinf0:
+                    data["status"] = 2
+                    _say(o, "Slow progress!")
+                    break
+                gap0, pinf0, dinf0 = gap, pinf, dinf
+            if it == int(o["ADMM_maxiter"]):
+                break
+            if r <= p - 1:  # :112-115
+                timed("rank", h.rank_cut, o["theta"], True)
+            nne = max(min(k.nneg, int(o["delta"])), 1)  # :116
+            staged = int(o["line_search"]) == 1
+            timed("escape", h.escape, nne, o["alpha"], int(o["line_search"]))
+            if pinf < o["tau1"] * gradnorm:  # :128-132
+                sigma = max(sigma / gama, o["sigma_min"])
+            elif pinf > o["tau2"] * gradnorm:
+                sigma = min(sigma * gama, o["sigma_max"])
+            h.set_sigma(sigma)
+        Y = h.get_Y()
+        y, _ = h.get_dual()
+        x, w = h.dual_state()
+        st = h.stats()
+        data["launches"] = st.launches_total
+        data["s_mode"], data["a_mode"] = st.s_mode, st.a_mode
+        data["phase_seconds"] = phase
+    X = S = None
+    if n <= DENSE_OUTPUT_MAX_N:
+        S = Y @ Y.T
+        dA = np.asarray(o["dAAt"], dtype=np.float64).ravel() if o.get("dAAt") is not None else \
+            np.asarray(Ap.multiply(Ap).sum(axis=1)).ravel()
+        eX = (x + Ap.T @ (bd / dA)).reshape(n, n, order="F")
+        X = eX - np.diag(np.sum(S * eX, axis=0))
+    data.update(X=X, y=y, S=S, w=w, x=x, gap=gap, pinf=pinf, dinf=dinf, gradnorm=gradnorm, time=time.perf_counter() - t0,
+                Y=Y, iters=it, obj=obj, sigma=sigma, lam_min=k.lam_min, lam_max=k.lam_max)
+    if data["status"] == 0 and eta > o["tol"]:
+        data["status"] = 1
+        _say(o, "Iteration maximum is reached!")
+    _say(o, f"ManiDSDP: optimum = {obj:0.8f}, time = {data['time']:0.2f}s")
+    return X, obj, data

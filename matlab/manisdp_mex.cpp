@@ -153,6 +153,18 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       pb.nob = (int32_t)mxGetScalar(prhs[7]);
       pb.block_sizes = blocks.data();
     }
+    if (pb.kind == MANISDP_DUAL_UNITDIAG) {
+      // manisdp_mex('create', 5, n, A(:,K.f+1:end)', b, c(K.f+1:end), dAAt, A(:,1:K.f), c(1:K.f))   (ManiDSDP_unitdiag.m:34-40)
+      if (nrhs > 6 && mxGetNumberOfElements(prhs[6]) > 0) pb.dAAt = mxGetPr(prhs[6]);
+      if (nrhs > 8 && mxGetN(prhs[7]) > 0) {
+        if (!mxIsSparse(prhs[7])) mexErrMsgIdAndTxt("ManiSDP:b200:arg", "B must be sparse");
+        pb.nfree = (int64_t)mxGetN(prhs[7]);
+        pb.B_jc = (const uint64_t*)mxGetJc(prhs[7]);
+        pb.B_ir = (const uint64_t*)mxGetIr(prhs[7]);
+        pb.B_pr = mxGetPr(prhs[7]);
+        pb.cf = mxGetPr(prhs[8]);
+      }
+    }
     manisdp_t* h = nullptr;
     manisdp_group_t* grp = nullptr;
     if (pb.kind == MANISDP_ONLYUNITDIAG && nrhs > 4 && mxGetNumberOfElements(prhs[4]) > 0) {
@@ -274,6 +286,17 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     CK(h, manisdp_hess(h), "hess");
     plhs[0] = mxCreateDoubleMatrix((mwSize)st.p, (mwSize)st.n, mxREAL);
     CK(h, manisdp_slot_get(h, MANISDP_SLOT_H, mxGetPr(plhs[0]), MANISDP_LAYOUT_ROWS), "slot_get");
+  } else if (c == "dual_state") {
+    // [x, w] = manisdp_mex('dual_state', h, nfree): the ADMM multipliers of a dual handle (x: n*n vector)
+    CK(h, manisdp_get_stats(h, &st), "get_stats");
+    const size_t nf = (size_t)mxGetScalar(prhs[2]);
+    plhs[0] = mxCreateDoubleMatrix((mwSize)(st.n * st.n), 1, mxREAL);
+    mxArray* w = mxCreateDoubleMatrix((mwSize)nf, 1, mxREAL);
+    CK(h, manisdp_dual_get_state(h, mxGetPr(plhs[0]), nf ? mxGetPr(w) : nullptr), "dual_get_state");
+    if (nlhs > 1)
+      plhs[1] = w;
+    else
+      mxDestroyArray(w);
   } else if (c == "mb_set_Y") {
     // Y: cell array, Y{i} is p_i x n_i (the layout of ManiSDP_multiblock.m; its memory image is n_i rows of p_i doubles)
     const mxArray* Y = prhs[2];

@@ -7,6 +7,7 @@ CPU restatement (NumPy/SciPy FP64, dense X / dense eig exactly as the reference 
   * src/primal/ManiSDP_unittrace.m      (closures :156-177, outer loop :52-117)
   * src/primal/ManiSDP.m                (closures :149-165, outer loop :52-113)
   * src/primal/ManiSDP_multiblock.m     (closures :203-247, outer loop :60-160, line search :180-201)
+  * src/dual/ManiDSDP_unitdiag.m        (closures :171-192, outer loop :63-141, line search :158-169)
 
 driving oracle/manopt_rtr.py in place of Manopt's trustregions.  It is the parity yardstick for the
 CUDA engine and the CPU baseline timed by bench.py; nothing in the product path imports it.
@@ -572,6 +573,148 @@ def ManiSDP_multiblock(At, b, c, K, options=None):
             sigma = min(sigma * gama, o["sigma_max"])
     data.update(X=X, y=y, S=S, gap=gap, pinf=pinf, dinf=dinf, gradnorm=gradnorm,
                 time=time.perf_counter() - t0, Y=Y, iters=it, obj=obj, sigma=sigma, dinfs=dinfs)
+    if data["status"] == 0 and eta > o["tol"]:
+        data["status"] = 1
+    return X, obj, data
+
+
+# --------------------------------------------------------------------------------------------
+# dual approach: Riemannian ADMM on the SOS form (src/dual/ManiDSDP_unitdiag.m)
+# --------------------------------------------------------------------------------------------
+DUAL_DEFAULTS = dict(p0=None, ADMM_maxiter=300, gama=2, sigma0=1e-3, sigma_min=1e-3, sigma_max=1e7, tol=1e-8,
+                     theta=1e-3, delta=8, alpha=0.1, tolgradnorm=1e-8, TR_maxinner=20, TR_maxiter=4, tau1=1e1,
+                     tau2=1e2, line_search=0)  # :10-26
+
+
+class DualProblem:
+    """Closures of ManiDSDP_unitdiag.m:171-192 on the oblique manifold (rows of Y are unit vectors, S = Y Y').
+    A: (m, n*n) PSD part of the constraint matrix, B: (m, K.f) free part, iA = (diag(dAAt) \\ A)'."""
+
+    def __init__(self, A, B, b, c, cf, n, p, dAAt, x, w, sigma):
+        self.A, self.B, self.b, self.c, self.cf, self.n = A, B, b, c, cf, n
+        self.iAt = sp.diags(1.0 / dAAt) @ A  # iA' = D^{-1} A   (:43)
+        self.bA = self.iAt.T @ b  # :44
+        self.x, self.w, self.sigma = x, w, sigma
+        self.M = ObliqueT(n, p)
+
+    def co(self, Y):  # :149-156
+        sc = _vec(Y @ Y.T) - self.c
+        y = self.iAt @ sc
+        As = self.A.T @ y - sc - self.x / self.sigma
+        Af = self.B.T @ y - self.cf - self.w / self.sigma
+        return float(self.b @ y + 0.5 * self.sigma * (As @ As + Af @ Af))
+
+    def cost(self, Y):  # :171-178
+        sc = _vec(Y @ Y.T) - self.c
+        y = self.iAt @ sc
+        self.As = self.A.T @ y - sc - self.x / self.sigma
+        Af = self.B.T @ y - self.cf - self.w / self.sigma
+        return float(self.b @ y + 0.5 * self.sigma * (self.As @ self.As + Af @ Af))
+
+    def accept(self, ok):
+        pass
+
+    def grad(self, Y):  # :180-184
+        self.X = _mat(self.bA - self.sigma * self.As, self.n)
+        eG = 2 * (self.X @ Y)
+        self.YeG = np.sum(Y * eG, axis=1, keepdims=True)
+        return eG - Y * self.YeG
+
+    def hess(self, Y, U):  # :186-191  (row layout: every product transposed)
+        s = self.sigma
+        YU = Y @ U.T  # (Y'*U)(a,b) = <Y_a, U_b>
+        yAU = _mat(self.A.T @ (self.iAt @ _vec(YU)), self.n)
+        eH = 2 * (self.X @ U) - 4 * s * (yAU.T @ Y) + 2 * s * (Y @ (U.T @ Y) + U @ (Y.T @ Y))
+        return eH - Y * np.sum(Y * eH, axis=1, keepdims=True) - U * self.YeG
+
+
+def ManiDSDP_unitdiag(A, b, c, K, options=None):
+    """[X, obj, data] of src/dual/ManiDSDP_unitdiag.m:8.  A: (m, K.f + n*n), c: (K.f + n*n,)."""
+    o = dict(DUAL_DEFAULTS)
+    o.update(options or {})
+    o.setdefault("seed", 0)
+    o.setdefault("verbose", False)
+    n = int(K["s"])
+    nf = int(K.get("f", 0))
+    A = sp.csr_matrix(A)
+    b = np.asarray(b, dtype=np.float64).ravel()
+    c = np.asarray(c.todense()).ravel() if sp.issparse(c) else np.asarray(c, dtype=np.float64).ravel()
+    if o["p0"] is None:
+        o["p0"] = int(math.ceil(math.log(len(b))))  # :11
+    normc = 1 + np.linalg.norm(c)  # :33
+    B = A[:, :nf].tocsr()
+    A = A[:, nf:].tocsr()
+    cf, c = c[:nf], c[nf:]
+    dAAt = np.asarray(o["dAAt"], dtype=np.float64).ravel() if o.get("dAAt") is not None else \
+        np.asarray(A.multiply(A).sum(axis=1)).ravel()  # :40
+    p = int(o["p0"])
+    sigma, gama = o["sigma0"], o["gama"]
+    x = np.zeros(n * n)
+    w = np.zeros(nf)
+    rng = np.random.default_rng(o["seed"])
+    Y = o.get("Y0")
+    if Y is not None:
+        Y = np.array(Y, dtype=np.float64)
+        p = Y.shape[1]
+    U = None
+    data = dict(status=0, hv_count=0, tr_iters=0, fac_size=[], seta=[])
+    t0 = time.perf_counter()
+    gap0 = pinf0 = dinf0 = None
+    for it in range(1, o["ADMM_maxiter"] + 1):
+        data["fac_size"].append(p)
+        prob = DualProblem(A, B, b, c, cf, n, p, dAAt, x, w, sigma)
+        if Y is None:
+            Y = prob.M.rand(rng)
+        if U is not None:
+            Y = _line_search("unitdiag", prob.co, Y, U)  # :66-68, :158-169
+        res = trustregions(prob, Y, maxiter=o["TR_maxiter"], maxinner=o["TR_maxinner"],
+                           tolgradnorm=o["tolgradnorm"])
+        Y = res.x
+        data["hv_count"] += res.hv_count
+        data["tr_iters"] += len(res.info) - 1
+        gradnorm = res.info[-1].gradnorm
+        S = Y @ Y.T  # :71-76
+        sc = _vec(S) - c
+        y = prob.iAt @ sc
+        As = A.T @ y - sc
+        Af = B.T @ y - cf
+        pinf = (np.linalg.norm(As) + np.linalg.norm(Af)) / normc
+        by = float(b @ y)
+        x = x - sigma * As  # :78-79
+        w = w - sigma * Af
+        eX = _mat(x + prob.bA, n)
+        z = np.sum(S * eX, axis=0)
+        X = eX - np.diag(z)
+        dX, vX = np.linalg.eigh(X)
+        obj = float(c @ _vec(eX) + cf @ w + z.sum())  # :86
+        dinf = max(0.0, -dX[0]) / (1 + abs(dX[-1]))
+        gap = abs(obj - by) / (1 + abs(obj) + abs(by))
+        Us, e, _ = np.linalg.svd(Y, full_matrices=False)
+        r = int(np.sum(e > o["theta"] * e[0]))  # :91 (strict)
+        if o["verbose"]:
+            print(f"Iter {it}, obj:{obj:0.8f}, gap:{gap:0.1e}, pinf:{pinf:0.1e}, dinf:{dinf:0.1e}, "
+                  f"gradnorm:{gradnorm:0.1e}, r:{r}, p:{p}, sigma:{sigma:0.3f}, "
+                  f"time:{time.perf_counter()-t0:0.2f}s")
+        eta = max(gap, pinf, dinf)
+        data["seta"].append(eta)
+        if eta < o["tol"]:
+            break
+        if it % 50 == 0:
+            if it > 100 and gap > gap0 and pinf > pinf0 and dinf > dinf0:
+                data["status"] = 2
+                break
+            gap0, pinf0, dinf0 = gap, pinf, dinf
+        if r <= p - 1:  # :112-115
+            Y, p = Us[:, :r] * e[:r], r
+        nne = max(min(int(np.sum(dX < 0)), o["delta"]), 1)  # :116
+        Y, U = _escape("unitdiag", o, Y, vX, nne)
+        p += nne
+        if pinf < o["tau1"] * gradnorm:
+            sigma = max(sigma / gama, o["sigma_min"])
+        elif pinf > o["tau2"] * gradnorm:
+            sigma = min(sigma * gama, o["sigma_max"])
+    data.update(X=X, y=y, S=S, w=w, x=x, gap=gap, pinf=pinf, dinf=dinf, gradnorm=gradnorm,
+                time=time.perf_counter() - t0, Y=Y, iters=it, obj=obj, sigma=sigma)
     if data["status"] == 0 and eta > o["tol"]:
         data["status"] = 1
     return X, obj, data

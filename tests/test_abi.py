@@ -29,7 +29,7 @@ def test_binding_covers_header(engine_lib):
 def test_struct_sizes_match_header():
     # sizes the MEX gateway / any FFI must agree on (LP64)
     from manisdp_matlab_b200 import _lib
-    assert ctypes.sizeof(_lib.Problem) == 8 + 16 + 3 * 8 + 3 * 8 + 8 + 8 + 8 + 8 + 8 + 16 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.Problem) == 8 + 16 + 3 * 8 + 3 * 8 + 8 + 8 + 8 + 8 + 8 + 16 + 8 + 8 + 8 + 8 + 6 * 8
     assert ctypes.sizeof(_lib.TrOptions) == 16 + 7 * 8
     assert ctypes.sizeof(_lib.TrInfo) == 4 * 8 + 8 + 16
     assert ctypes.sizeof(_lib.TrIter) == 5 * 8 + 16

@@ -29,7 +29,8 @@ def test_matlab_drivers_keep_reference_signatures():
             "ManiSDP_unitdiag.m": "function [X, obj, data] = ManiSDP_unitdiag(At, b, c, K, options)",
             "ManiSDP_unittrace.m": "function [X, obj, data] = ManiSDP_unittrace(At, b, c, K, options)",
             "ManiSDP.m": "function [X, obj, data] = ManiSDP(At, b, c, K, options)",
-            "ManiSDP_multiblock.m": "function [X, obj, data] = ManiSDP_multiblock(At, b, c, K, options)"}
+            "ManiSDP_multiblock.m": "function [X, obj, data] = ManiSDP_multiblock(At, b, c, K, options)",
+            "ManiDSDP_unitdiag.m": "function [X, obj, data] = ManiDSDP_unitdiag(A, b, c, K, options)"}
     for f, s in sigs.items():
         assert open(os.path.join(ROOT, "matlab", f)).readline().strip() == s
 
