@@ -249,6 +249,7 @@ template <int GS, int VPL>
 __global__ void __launch_bounds__(MSDP_THREADS) k_rowlist_apply(RowlistArgs a, RtrState* st) {
   if (a.pred && *a.pred == 0) return;
   if (a.skip_if_stopped && st->stop != 0) return;
+  const unsigned mask = group_mask<GS>();
   const int gl = threadIdx.x % GS, nvec = a.ld / 2, ld = a.ld;
   const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / GS);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / GS) + threadIdx.x / GS; row < a.nrows; row += ngroups) {
@@ -271,24 +272,75 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_rowlist_apply(RowlistArgs a, R
       }
     }
     if (a.ra) {
-      for (int e = a.rptr[row]; e < a.rptr[row + 1]; ++e) {
-        const double av = __ldg(a.ra + e);
-        const int j = __ldg(a.rj + e), k = __ldg(a.rk + e);
-        const double w1 = a.vec1 ? a.c1 * av * __ldg(a.vec1 + k) : 0.0;
-        const double w2 = a.vec2 ? a.c2 * av * __ldg(a.vec2 + k) : 0.0;
+      // The entries of a row are taken GS at a time: lane l of the row group loads entry eb + l (coalesced index / value
+      // loads, then the multiplier gathers vec[k]) and the group walks the batch through shuffles, four entries per step
+      // with all their operand-row gathers in flight together.  Summation order is the entry order (V1 term, then V2
+      // term), exactly as a one-by-one walk -- results do not depend on the batching.  Long rows (a dense block of a
+      // multi-block moment relaxation has hundreds of entries per row) used to cost three dependent round trips per entry.
+      const int e0 = a.rptr[row], e1 = a.rptr[row + 1];
+      for (int eb = e0; eb < e1; eb += GS) {
+        const int e = eb + gl;
+        int j = 0;
+        double w1 = 0.0, w2 = 0.0;
+        if (e < e1) {
+          const double av = __ldg(a.ra + e);
+          j = __ldg(a.rj + e);
+          const int k = __ldg(a.rk + e);
+          if (a.vec1) w1 = a.c1 * av * __ldg(a.vec1 + k);
+          if (a.vec2) w2 = a.c2 * av * __ldg(a.vec2 + k);
+        }
+        const int cnt = min(GS, e1 - eb);
+        int u = 0;
+        for (; u + 4 <= cnt; u += 4) {
+          size_t jo[4];
+          double a1[4], a2[4];
 #pragma unroll
-        for (int t = 0; t < VPL; ++t) {
-          const int c = gl + GS * t;
-          if (c < nvec) {
-            if (a.vec1) {
-              const double2 u = ldg2(a.V1 + (size_t)j * ld + 2 * c);
-              acc[t].x = fma(w1, u.x, acc[t].x);
-              acc[t].y = fma(w1, u.y, acc[t].y);
+          for (int q = 0; q < 4; ++q) {
+            jo[q] = (size_t)__shfl_sync(mask, j, u + q, GS) * ld;
+            a1[q] = __shfl_sync(mask, w1, u + q, GS);
+            a2[q] = __shfl_sync(mask, w2, u + q, GS);
+          }
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) {
+            const int c = gl + GS * t;
+            if (c < nvec) {
+              double2 x1[4], x2[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (a.vec1) x1[q] = ldg2(a.V1 + jo[q] + 2 * c);
+                if (a.vec2) x2[q] = ldg2(a.V2 + jo[q] + 2 * c);
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (a.vec1) {
+                  acc[t].x = fma(a1[q], x1[q].x, acc[t].x);
+                  acc[t].y = fma(a1[q], x1[q].y, acc[t].y);
+                }
+                if (a.vec2) {
+                  acc[t].x = fma(a2[q], x2[q].x, acc[t].x);
+                  acc[t].y = fma(a2[q], x2[q].y, acc[t].y);
+                }
+              }
             }
-            if (a.vec2) {
-              const double2 u = ldg2(a.V2 + (size_t)j * ld + 2 * c);
-              acc[t].x = fma(w2, u.x, acc[t].x);
-              acc[t].y = fma(w2, u.y, acc[t].y);
+          }
+        }
+        for (; u < cnt; ++u) {
+          const size_t jo = (size_t)__shfl_sync(mask, j, u, GS) * ld;
+          const double b1 = __shfl_sync(mask, w1, u, GS), b2 = __shfl_sync(mask, w2, u, GS);
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) {
+            const int c = gl + GS * t;
+            if (c < nvec) {
+              if (a.vec1) {
+                const double2 x = ldg2(a.V1 + jo + 2 * c);
+                acc[t].x = fma(b1, x.x, acc[t].x);
+                acc[t].y = fma(b1, x.y, acc[t].y);
+              }
+              if (a.vec2) {
+                const double2 x = ldg2(a.V2 + jo + 2 * c);
+                acc[t].x = fma(b2, x.x, acc[t].x);
+                acc[t].y = fma(b2, x.y, acc[t].y);
+              }
             }
           }
         }

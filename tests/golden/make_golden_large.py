@@ -5,7 +5,7 @@
     is recorded so that the GPU test proves it solved the same instance.  Options of example/example_qsphere.m:21-27.
   * config 2: BQP q = 60 (n = 1831, m = 1 155 281), data/bqp_{Q,e}_60_1.txt, options of example/example_bqp.m:31-41.
 
-    python tests/golden/make_golden_large.py [qs60] [bqp60] [bqpsparse]
+    python tests/golden/make_golden_large.py [qs60] [bqp60] [bqpsparse] [bqpdual60]
 
   * multi-block: the sparse BQP of example/example_bqp_sparse.m (20 blocks of order 211) through ManiSDP_multiblock.
 
@@ -80,7 +80,27 @@ def bqpsparse():
                                    oracle_seconds=time.perf_counter() - t0))
 
 
+def bqpdual60():
+    """dual approach on config 2's instance: example/dual/example_bqp_dual.m:19-36 on data/bqp_{Q,e}_60_1.txt
+    (SOS form, n = 1831, m = 523 686 monomials); the optimum equals the primal KAT -520.38067984 (strong duality)"""
+    import scipy.sparse as sp
+    d = np.load(f"{HERE}/bqp_60_1.npz")
+    A, b, dAAt, mb = g.bqpsos(d["Q"], d["e"], 60)
+    v = np.zeros((A.shape[0], 1))
+    v[0] = 1.0
+    A2 = sp.hstack([sp.csr_matrix(v), A]).tocsr()
+    c = np.concatenate([[1.0], np.zeros(mb * mb)])
+    maxb = float(np.abs(b).max())
+    opts = dict(tol=1e-8, line_search=1)
+    t0 = time.perf_counter()
+    X, obj, data = ref.ManiDSDP_unitdiag(A2, b / maxb, c, {"f": 1, "s": mb}, dict(opts, dAAt=dAAt, seed=0))
+    merge("bqp_60_1_dual", dict(options=opts, status=int(data["status"]), obj=obj * maxb, obj_scaled=obj,
+                                eta=max(data["gap"], data["pinf"], data["dinf"]), hv=data["hv_count"],
+                                iters=data["iters"], n=int(mb), m=int(A2.shape[0]),
+                                oracle_seconds=time.perf_counter() - t0))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["qs60", "bqp60", "bqpsparse"]
+    which = sys.argv[1:] or ["qs60", "bqp60", "bqpsparse", "bqpdual60"]
     for w in which:
-        {"qs60": qs60, "bqp60": bqp60, "bqpsparse": bqpsparse}[w]()
+        {"qs60": qs60, "bqp60": bqp60, "bqpsparse": bqpsparse, "bqpdual60": bqpdual60}[w]()

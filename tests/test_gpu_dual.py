@@ -192,3 +192,18 @@ def test_dual_full_solve_bqp20_matches_oracle_and_primal(line_search):
     _, obj_p, dp = ManiSDP_unitdiag(At, bp, cp / mc, Kp, dict(tol=1e-8, verbose=False))
     assert dp["status"] == 0
     assert abs(obj * maxb - obj_p * mc) <= 1e-5 * abs(obj_p * mc)
+
+
+def test_dual_bqp60_reaches_the_baseline_optimum():
+    """config 2's instance (data/bqp_{Q,e}_60_1.txt, n = 1831) through the DUAL driver at its stated size: the optimum
+    equals BASELINE.md's KAT -520.38067984 (strong duality with the moment relaxation) and the oracle's dual run
+    (tests/golden/make_golden_large.py bqpdual60), all residues <= 1e-8"""
+    import json
+    from manisdp_matlab_b200 import ManiDSDP_unitdiag
+    gold = json.load(open(os.path.join(GOLDEN, "oracle_outputs_large.json")))
+    A2, b, c, K, dAAt, maxb, _ = _sos(60)
+    assert (K["s"], A2.shape[0]) == (gold["bqp_60_1_dual"]["n"], gold["bqp_60_1_dual"]["m"])
+    _, obj, data = ManiDSDP_unitdiag(A2, b, c, K, dict(dAAt=dAAt, tol=1e-8, line_search=1, verbose=False))
+    assert data["status"] == 0 and max(data["gap"], data["pinf"], data["dinf"]) < 1e-8
+    assert abs(obj * maxb - gold["bqp_60_1_dual"]["obj"]) <= 1e-6 * abs(gold["bqp_60_1_dual"]["obj"])
+    assert abs(obj * maxb - gold["bqp_60_1_opt"]["obj"]) <= 1e-6 * abs(gold["bqp_60_1_opt"]["obj"])

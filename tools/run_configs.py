@@ -42,7 +42,7 @@ def run(name, cpu):
         opts = dict(p0=64, delta=8)
         call = lambda mod, o: mod.ManiSDP_onlyunitdiag(C, o)
         n, m = nn, nn
-    elif name.startswith("bqp"):
+    elif name.startswith("bqp") and name[3:].isdigit():
         q = int(name[3:])
         d = np.load(os.path.join(GOLDEN, f"bqp_{q}_1.npz"))
         At, b, c, K = g.bqpmom(q, d["Q"], d["e"])
@@ -77,6 +77,24 @@ def run(name, cpu):
         opts = dict(tol=1e-8, line_search=1, tau1=1)
         call = lambda mod, o: mod.ManiSDP_multiblock(At, b, c, K, o)
         n, m = int(sum(K["s"])), At.shape[1]
+    elif name.startswith("bqpdual"):  # dual approach: example/dual/example_bqp_dual.m on data/bqp_{Q,e}_<q>_1.txt
+        import scipy.sparse as sp_
+        from instances import generators as gi
+        q = int(name[len("bqpdual"):])
+        d = np.load(os.path.join(GOLDEN, f"bqp_{q}_1.npz"))
+        A, bb, dAAt, mb = gi.bqpsos(d["Q"], d["e"], q)
+        v = np.zeros((A.shape[0], 1))
+        v[0] = 1.0
+        A2 = sp_.hstack([sp_.csr_matrix(v), A]).tocsr()
+        c = np.concatenate([[1.0], np.zeros(mb * mb)])
+        maxb = float(np.abs(bb).max())
+        b, K = bb / maxb, {"f": 1, "s": mb}
+        opts = dict(dAAt=dAAt, tol=1e-8, line_search=1)
+
+        def call(mod, o, _A=A2, _b=b, _c=c, _K=K, _s=maxb):
+            X_, obj_, data_ = mod.ManiDSDP_unitdiag(_A, _b, _c, _K, o)
+            return X_, obj_ * _s, data_
+        n, m = mb, A2.shape[0]
     elif name == "demo1":  # multi-block: data/test.m on data/SDP_demo_1.mat (89 blocks, K.nob = 0)
         import scipy.sparse as sp_
         d = np.load(os.path.join(GOLDEN, "sdp_demo_1.npz"))
@@ -113,11 +131,11 @@ def run(name, cpu):
     rec = dict(config=name, n=n, m=m, seconds=dt, obj=obj, eta=eta, iters=data["iters"], hv=int(data["hv_count"]),
                tr_seconds=data["tr_seconds"], hv_per_s=data["hv_count"] / max(data["tr_seconds"], 1e-9),
                status=data["status"], launches=int(data.get("launches", 0)), gen_seconds=t_gen,
-               modes=[data.get("s_mode"), data.get("a_mode")], p_max=max(data["fac_size"]),
+               modes=[data.get("s_mode"), data.get("a_mode")], p_max=int(np.max([np.max(v) for v in data["fac_size"]])),
                kkt_seconds=data.get("kkt_seconds"), eig_iters=data.get("eig_iters_total"),
                setup_seconds=data.get("setup_seconds"), fac_size=data["fac_size"] if np.ndim(data["fac_size"]) == 1 else [max(v) for v in data["fac_size"]],
                phase_seconds=data.get("phase_seconds"),
-               options={k: v for k, v in o.items() if k not in ("verbose", "nccl_id")}, n_gpus=world)
+               options={k: v for k, v in o.items() if k not in ("verbose", "nccl_id", "dAAt")}, n_gpus=world)
     if world > 1 and int(os.environ["RANK"]) != 0:
         return
     if cpu:
