@@ -12,6 +12,7 @@
 // Index arithmetic: At rows are 64-bit linear indices r = j*n + i, split with integer div/mod at create time (bit-exact).
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <numeric>
 #include "affine.h"
@@ -359,6 +360,130 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_rowlist_apply(RowlistArgs a, R
         st2(a.out + rb + 2 * c, acc[t]);
       }
     }
+  }
+}
+
+// K3 for LONG rows (dense blocks of a multi-block moment relaxation: hundreds of entries per row, few thousand rows): one
+// CTA per row.  Warp w of the CTA takes the 32-entry batches w, w + 8, w + 16, ... of the row (same batched walk as
+// above), the eight partial rows meet in shared memory and are added in warp order -- a fixed summation tree, so results
+// are reproducible -- together with the C part, alpha / beta and the store.  One warp per row left the SMs a third full
+// and every warp walking ~11 dependent batches; this form has 8x the loads in flight per row.
+template <int VPL>
+__global__ void __launch_bounds__(MSDP_THREADS) k_rowlist_apply_wide(RowlistArgs a, RtrState* st) {
+  __shared__ double2 part[MSDP_THREADS / 32][MSDP_MAX_LD / 2];
+  if (a.pred && *a.pred == 0) return;
+  if (a.skip_if_stopped && st->stop != 0) return;
+  constexpr int GS = 32, NW = MSDP_THREADS / 32;
+  const int gl = threadIdx.x % 32, wid = threadIdx.x / 32, nvec = a.ld / 2, ld = a.ld;
+  for (int64_t row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+    double2 acc[VPL];
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) acc[t] = make_double2(0.0, 0.0);
+    if (a.cval && wid == 0) {
+      for (int e = a.crowptr[row]; e < a.crowptr[row + 1]; ++e) {
+        const double w = a.alphaC * __ldg(a.cval + e);
+        const double* pj = a.V1 + (size_t)__ldg(a.ccol + e) * ld;
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) {
+          const int c = gl + GS * t;
+          if (c < nvec) {
+            const double2 u = ldg2(pj + 2 * c);
+            acc[t].x = fma(w, u.x, acc[t].x);
+            acc[t].y = fma(w, u.y, acc[t].y);
+          }
+        }
+      }
+    }
+    const int e0 = a.rptr[row], e1 = a.rptr[row + 1];
+    for (int eb = e0 + GS * wid; eb < e1; eb += GS * NW) {
+      const int e = eb + gl;
+      int j = 0;
+      double w1 = 0.0, w2 = 0.0;
+      if (e < e1) {
+        const double av = __ldg(a.ra + e);
+        j = __ldg(a.rj + e);
+        const int k = __ldg(a.rk + e);
+        if (a.vec1) w1 = a.c1 * av * __ldg(a.vec1 + k);
+        if (a.vec2) w2 = a.c2 * av * __ldg(a.vec2 + k);
+      }
+      const int cnt = min(GS, e1 - eb);
+      int u = 0;
+      for (; u + 4 <= cnt; u += 4) {
+        size_t jo[4];
+        double a1[4], a2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          jo[q] = (size_t)__shfl_sync(0xffffffffu, j, u + q) * ld;
+          a1[q] = __shfl_sync(0xffffffffu, w1, u + q);
+          a2[q] = __shfl_sync(0xffffffffu, w2, u + q);
+        }
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) {
+          const int c = gl + GS * t;
+          if (c < nvec) {
+            double2 x1[4], x2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (a.vec1) x1[q] = ldg2(a.V1 + jo[q] + 2 * c);
+              if (a.vec2) x2[q] = ldg2(a.V2 + jo[q] + 2 * c);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (a.vec1) {
+                acc[t].x = fma(a1[q], x1[q].x, acc[t].x);
+                acc[t].y = fma(a1[q], x1[q].y, acc[t].y);
+              }
+              if (a.vec2) {
+                acc[t].x = fma(a2[q], x2[q].x, acc[t].x);
+                acc[t].y = fma(a2[q], x2[q].y, acc[t].y);
+              }
+            }
+          }
+        }
+      }
+      for (; u < cnt; ++u) {
+        const size_t jo = (size_t)__shfl_sync(0xffffffffu, j, u) * ld;
+        const double b1 = __shfl_sync(0xffffffffu, w1, u), b2 = __shfl_sync(0xffffffffu, w2, u);
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) {
+          const int c = gl + GS * t;
+          if (c < nvec) {
+            if (a.vec1) {
+              const double2 x = ldg2(a.V1 + jo + 2 * c);
+              acc[t].x = fma(b1, x.x, acc[t].x);
+              acc[t].y = fma(b1, x.y, acc[t].y);
+            }
+            if (a.vec2) {
+              const double2 x = ldg2(a.V2 + jo + 2 * c);
+              acc[t].x = fma(b2, x.x, acc[t].x);
+              acc[t].y = fma(b2, x.y, acc[t].y);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const int c = gl + GS * t;
+      if (c < nvec) part[wid][c] = acc[t];
+    }
+    __syncthreads();
+    const size_t rb = (size_t)row * ld;
+    for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
+      double2 sres = part[0][c];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) {
+        sres.x += part[w][c].x;
+        sres.y += part[w][c].y;
+      }
+      if (a.beta != 0.0) {
+        const double2 o = ld2(a.out + rb + 2 * c);
+        sres.x = fma(a.beta, o.x, sres.x);
+        sres.y = fma(a.beta, o.y, sres.y);
+      }
+      st2(a.out + rb + 2 * c, sres);
+    }
+    __syncthreads();
   }
 }
 
@@ -877,6 +1002,16 @@ static int apply_S_sparse(manisdp_handle* h, const double* V1, const double* vec
   a.ld = ld;
   a.pred = pred;
   a.skip_if_stopped = skip_if_stopped;
+  // long rows (on average >= 64 entries) and full-warp row groups: one CTA per row
+  static const int wide_on = getenv("MANISDP_K3_WIDE") ? atoi(getenv("MANISDP_K3_WIDE")) : 1;  // A/B switch
+  if (wide_on && h->As.nnz >= 64 * h->n && ld >= 64 && h->n <= (int64_t)h->num_sms * 64) {
+    const int nb = (int)std::min<int64_t>(h->n, (int64_t)h->num_sms * 8);
+    DISPATCH_GEOM(row_geom(ld), {
+      if (GS == 32) k_rowlist_apply_wide<VPL><<<nb, MSDP_THREADS, 0, h->stream>>>(a, h->st);
+    });
+    KERNEL_CHECK(h);
+    return MANISDP_OK;
+  }
   DISPATCH_GEOM(row_geom(ld), {
     k_rowlist_apply<GS, VPL><<<rows_grid(h, h->n, GS), MSDP_THREADS, 0, h->stream>>>(a, h->st);
   });

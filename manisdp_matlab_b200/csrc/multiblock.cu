@@ -20,6 +20,19 @@
 #include "kernels.cuh"
 #include "rowops.cuh"
 #include "small_eig.h"
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
+
+// per-phase wall seconds of the block-aware steps, printed at destroy when MANISDP_EIG_DEBUG is set
+static double g_mb_resid_s = 0.0, g_mb_slack_s = 0.0, g_mb_eig_s = 0.0, g_mb_update_s = 0.0;
+static long g_mb_kkt_calls = 0;
+struct MbSeconds {
+  double& acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit MbSeconds(double& a) : acc(a) {}
+  ~MbSeconds() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 // ---- kernels ------------------------------------------------------------------------------------------------------------
 // columns >= p[block(row)] <- 0
@@ -136,6 +149,12 @@ int msdp_mb_setup(manisdp_handle* h, const manisdp_problem* pb) {
 }
 
 void msdp_mb_free(manisdp_handle* h) {
+  if (h->kind == MANISDP_MULTIBLOCK && g_mb_kkt_calls > 0 && getenv("MANISDP_EIG_DEBUG")) {
+    fprintf(stderr, "[manisdp multiblock] %ld kkt steps: residues %.3f s, slack blocks (S*I + copy) %.3f s, eig of the blocks "
+                    "%.3f s; rank cut + escape %.3f s\n", g_mb_kkt_calls, g_mb_resid_s, g_mb_slack_s, g_mb_eig_s, g_mb_update_s);
+    g_mb_kkt_calls = 0;
+    g_mb_resid_s = g_mb_slack_s = g_mb_eig_s = g_mb_update_s = 0.0;
+  }
   if (h->mb_rowblk) cudaFree(h->mb_rowblk);
   if (h->mb_roff_dev) cudaFree(h->mb_roff_dev);
   if (h->mb_pw) cudaFree(h->mb_pw);
@@ -238,7 +257,11 @@ extern "C" int manisdp_mb_kkt(manisdp_t* h, int32_t update_dual, manisdp_kkt_inf
   CUDA_TRY(h, cudaSetDevice(h->device));
   memset(out, 0, sizeof(*out));
   // obj, pinf, y <- y - sigma*Axb, by = b'y + sum of z over the unit-diagonal blocks (:73-79, :84-88); zdiag holds z
-  MSDP_TRY(msdp_affine_kkt(h, update_dual, out));
+  g_mb_kkt_calls++;
+  {
+    MbSeconds t(g_mb_resid_s);
+    MSDP_TRY(msdp_affine_kkt(h, update_dual, out));
+  }
   // S{i} of every block: S * (stacked identity) -- S is block diagonal, so the rows of block i hold S{i} (:81-89)
   const int t = (int)h->mb_n.size();
   int64_t nmax = 0;
@@ -249,6 +272,7 @@ extern "C" int manisdp_mb_kkt(manisdp_t* h, int32_t update_dual, manisdp_kkt_inf
   MSDP_TRY(msdp_scratch(h, 1, (size_t)h->n * kc * sizeof(double), (void**)&AV));
   std::vector<double> Sb((size_t)h->mb_off2[t], 0.0);  // S{i}, row-major n_i x n_i, at mb_off2[i]
   std::vector<double> stage((size_t)h->n * kc);
+  const auto t_slack0 = std::chrono::steady_clock::now();
   for (int64_t c0 = 0; c0 < nmax; c0 += kc) {
     k_mb_identity<<<mb_grid(h, h->n * kc), MSDP_THREADS, 0, h->stream>>>(V, h->mb_rowblk, h->mb_roff_dev, h->n, kc, (int)c0);
     KERNEL_CHECK(h);
@@ -263,6 +287,8 @@ extern "C" int manisdp_mb_kkt(manisdp_t* h, int32_t update_dual, manisdp_kkt_inf
                (size_t)cw * sizeof(double));
     }
   }
+  g_mb_slack_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_slack0).count();
+  MbSeconds teig(g_mb_eig_s);
   // eig(S{i}, 'vector') of every block (:90): one dense symmetric eigen-decomposition per block, blocks spread over host
   // threads (the blocks of a multi-block SDP are small -- 10..200 here -- and independent)
   h->mb_evals.assign((size_t)h->n, 0.0);
@@ -274,7 +300,7 @@ extern "C" int manisdp_mb_kkt(manisdp_t* h, int32_t update_dual, manisdp_kkt_inf
     const double* S = &Sb[(size_t)h->mb_off2[i]];
     for (int a = 0; a < ni; ++a)
       for (int b = 0; b < ni; ++b) A[(size_t)a * ni + b] = 0.5 * (S[(size_t)a * ni + b] + S[(size_t)b * ni + a]);
-    if (!sym_eig(A, ni, ev, Z)) {
+    if (!sym_eig(A, ni, ev, Z, true, t >= 4 ? 1 : 0)) {  // many blocks: one decomposition per thread, no nested threads
       ok[(size_t)i] = 0;
       return;
     }
@@ -345,6 +371,7 @@ extern "C" int manisdp_mb_update(manisdp_t* h, double theta, int32_t delta, doub
   if (!h->mb_have_eigs) return msdp_fail(h, MANISDP_E_STATE, "mb_update: call manisdp_mb_kkt first");
   if (delta < 0) return msdp_fail(h, MANISDP_E_ARG, "mb_update: delta must be >= 0");
   NvtxRange nvtx_range("manisdp:mb_update");
+  MbSeconds tupd(g_mb_update_s);
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int t = (int)h->mb_n.size();
   const int ldo = (int)h->ld;
@@ -359,21 +386,30 @@ extern "C" int manisdp_mb_update(manisdp_t* h, double theta, int32_t delta, doub
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   std::vector<int> pold(h->mb_p.begin(), h->mb_p.end()), rcut((size_t)t), nne((size_t)t, 0);
   std::vector<std::vector<double>> W((size_t)t);  // truncation basis of the blocks that are cut: p_i x r_i, row-major
-  for (int i = 0; i < t; ++i) {
+  std::vector<int> okb((size_t)t, 1);
+  auto block_rules = [&](int i) {
     const int pi = pold[(size_t)i], ni = (int)h->mb_n[i];
     rcut[(size_t)i] = pi;
-    if (ni < min_facsize) continue;  // :115
-    if (pi > 1) {                    // :116-129
+    if (ni < min_facsize) return;  // :115
+    if (pi > 1) {                  // :116-129
       std::vector<double> A((size_t)pi * pi), ev, Z;
       const double* Gb = &G[(size_t)i * ldo * ldo];
       for (int a = 0; a < pi; ++a)
         for (int b = a; b < pi; ++b) A[(size_t)a * pi + b] = A[(size_t)b * pi + a] = Gb[(size_t)a * ldo + b];
-      if (!sym_eig(A, pi, ev, Z)) return msdp_fail(h, MANISDP_E_NUMERIC, "mb_update: Gram eigen-decomposition failed");
+      // eigenvalues first (cheap); the basis only when the block is actually cut
+      if (!sym_eig(A, pi, ev, Z, false, 1)) {
+        okb[(size_t)i] = 0;
+        return;
+      }
       const double s1 = sqrt(std::max(0.0, ev[(size_t)pi - 1]));
       int r = 0;
       for (int a = 0; a < pi; ++a) r += (sqrt(std::max(0.0, ev[(size_t)a])) >= theta * s1);  // :123
       if (r == 0) r = 1;                                                                      // :124-126
       if (r < pi) {  // :127-130: Y{i} = diag(e(1:r))*V(:,1:r)'  ==  (row layout) Y_i * W(:, 1:r), singular values descending
+        if (!sym_eig(A, pi, ev, Z, true, 1)) {
+          okb[(size_t)i] = 0;
+          return;
+        }
         W[(size_t)i].assign((size_t)pi * r, 0.0);
         for (int q = 0; q < pi; ++q)
           for (int c = 0; c < r; ++c) W[(size_t)i][(size_t)q * r + c] = Z[(size_t)q * pi + (pi - 1 - c)];
@@ -387,7 +423,23 @@ extern "C" int manisdp_mb_update(manisdp_t* h, double theta, int32_t delta, doub
     if (i < h->mb_nob) ne = std::max(ne, 1);        // :131-135
     if (rcut[(size_t)i] + ne > ni) ne = 0;          // :136-138
     nne[(size_t)i] = ne;
+  };
+  {  // the blocks are independent: spread them over host threads
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int T = (int)std::min<unsigned>({hw, 16u, (unsigned)t});
+    if (T <= 1) {
+      for (int i = 0; i < t; ++i) block_rules(i);
+    } else {
+      std::vector<std::thread> th;
+      for (int w = 0; w < T; ++w)
+        th.emplace_back([&, w]() {
+          for (int i = w; i < t; i += T) block_rules(i);
+        });
+      for (auto& x : th) x.join();
+    }
   }
+  for (int i = 0; i < t; ++i)
+    if (!okb[(size_t)i]) return msdp_fail(h, MANISDP_E_NUMERIC, "mb_update: Gram eigen-decomposition failed");
   int64_t pmax = 1;
   std::vector<int64_t> pn((size_t)t);
   int nemax = 0;

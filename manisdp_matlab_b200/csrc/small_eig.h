@@ -76,8 +76,10 @@ MSDP_EIG_CLONES inline void sym_eig_apply_rotations(double* V, int n, const std:
 // ascending order.  Returns false if QL fails to converge (never observed; 60 sweeps per eigenvalue allowed).
 // want_vectors = false: eigenvalues only (skips the accumulation of the Householder reflectors and the rotation
 // updates, ~5x cheaper); V is then scratch.
+// max_threads: upper bound on the host threads of the rotation phase (0: automatic; 1 when the caller already runs one
+// decomposition per thread, e.g. the blocks of a multi-block SDP).
 MSDP_EIG_CLONES inline bool sym_eig(const std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& V,
-                    bool want_vectors = true) {
+                    bool want_vectors = true, int max_threads = 0) {
   V = A;
   w.assign(n, 0.0);
   std::vector<double> e(n, 0.0);
@@ -239,6 +241,7 @@ MSDP_EIG_CLONES inline bool sym_eig(const std::vector<double>& A, int n, std::ve
       const unsigned hw = std::thread::hardware_concurrency();
       T = (int)std::max(1u, std::min(8u, hw / 2));
       T = std::min(T, std::max(1, n / 32));
+      if (max_threads > 0) T = std::min(T, max_threads);
     }
     if (T <= 1) {
       sym_eig_apply_rotations(V.data(), n, rot, 0, n);
