@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-MANISDP_K3_WIDE=0 timeout 300 python tools/run_configs.py bqpsparse:20x20 --verbose --opts='{"AL_maxiter": 40}' 2>&1 | grep "^Iter" | cut -c1-150 > gpurun_out/mb_off.txt
-MANISDP_K3_WIDE=1 timeout 300 python tools/run_configs.py bqpsparse:20x20 --verbose --opts='{"AL_maxiter": 40}' 2>&1 | grep "^Iter" | cut -c1-150 > gpurun_out/mb_on.txt
-paste -d'\n' gpurun_out/mb_off.txt gpurun_out/mb_on.txt | sed 's/, time:.*//' | head -80
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r2_pytest_full3.log 2>&1; tail -6 gpurun_out/r2_pytest_full3.log
+timeout 900 python bench.py > gpurun_out/r2_bench_n1_b.json 2> gpurun_out/r2_bench_n1_b.err; tail -c 3000 gpurun_out/r2_bench_n1_b.json; tail -3 gpurun_out/r2_bench_n1_b.err
