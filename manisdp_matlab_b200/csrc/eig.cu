@@ -8,6 +8,7 @@
 #include <algorithm>
 #include "affine.h"
 #include "dist.h"
+#include "gemm.h"
 #include "kernels.cuh"
 #include "rowops.cuh"
 #include "small_eig.h"
@@ -492,8 +493,71 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
           Gs[(size_t)a * m + b] = g * dscale[a] * dscale[b];
           As[(size_t)a * m + b] = sgn * ga * dscale[a] * dscale[b];
         }
+      // Fast path: Cholesky of the unit-diagonal Gram matrix (Gs = L L'), At = L^-1 As L^-T, ONE small eigen-solve.  When a
+      // squared pivot falls below 1e-3 (a W or P column close to the span of the others -- typical near convergence and on
+      // the highly degenerate spectra of theta SDPs, where a looser bound was measured to stall the solve) the canonical orthogonalisation
+      // below takes over.  The fast path halves the host time of an iteration (two 36 x 36 decompositions were ~80 % of it:
+      // 52 500 iterations on the q = 60 quartic, 9.8 s of its 22.6 s).
+      {
+        std::vector<double> L((size_t)m * m, 0.0);
+        bool chol_ok = true;
+        for (int a = 0; a < m && chol_ok; ++a) {
+          for (int b = 0; b <= a; ++b) {
+            double sum = Gs[(size_t)a * m + b];
+            for (int q = 0; q < b; ++q) sum -= L[(size_t)a * m + q] * L[(size_t)b * m + q];
+            if (a == b) {
+              if (!(sum > 1e-3)) {
+                chol_ok = false;
+                break;
+              }
+              L[(size_t)a * m + a] = sqrt(sum);
+            } else {
+              L[(size_t)a * m + b] = sum / L[(size_t)b * m + b];
+            }
+          }
+        }
+        if (chol_ok) {
+          // T1 = L^-1 As  (forward substitution, column by column), At = T1 L^-T = (L^-1 T1')'
+          std::vector<double> T1((size_t)m * m), At((size_t)m * m);
+          for (int c = 0; c < m; ++c)
+            for (int a = 0; a < m; ++a) {
+              double sum = As[(size_t)a * m + c];
+              for (int q = 0; q < a; ++q) sum -= L[(size_t)a * m + q] * T1[(size_t)q * m + c];
+              T1[(size_t)a * m + c] = sum / L[(size_t)a * m + a];
+            }
+          for (int r = 0; r < m; ++r)      // row r of T1, solve L x = T1(r, :)'  ->  At(r, :) = x'
+            for (int a = 0; a < m; ++a) {
+              double sum = T1[(size_t)r * m + a];
+              for (int q = 0; q < a; ++q) sum -= L[(size_t)a * m + q] * At[(size_t)r * m + q];
+              At[(size_t)r * m + a] = sum / L[(size_t)a * m + a];
+            }
+          for (int r = 0; r < m; ++r)
+            for (int q = r + 1; q < m; ++q) {
+              const double v = 0.5 * (At[(size_t)r * m + q] + At[(size_t)q * m + r]);
+              At[(size_t)r * m + q] = At[(size_t)q * m + r] = v;
+            }
+          std::vector<double> ev, Zt;
+          bool okeig = sym_eig(At, m, ev, Zt);
+          for (int c = 0; okeig && c < k; ++c) okeig = std::isfinite(ev[c]);
+          if (okeig) {
+            // C = L^-T Zt(:, 0:k)  (back substitution), then undo the diagonal scaling
+            Cfull.assign((size_t)m * k, 0.0);
+            for (int c = 0; c < k; ++c)
+              for (int a = m - 1; a >= 0; --a) {
+                double sum = Zt[(size_t)a * m + c];
+                for (int q = a + 1; q < m; ++q) sum -= L[(size_t)q * m + a] * Cfull[(size_t)q * k + c];
+                Cfull[(size_t)a * k + c] = sum / L[(size_t)a * m + a];
+              }
+            for (int a = 0; a < m; ++a)
+              for (int c = 0; c < k; ++c) Cfull[(size_t)a * k + c] *= dscale[a];
+            ritz.assign(ev.begin(), ev.begin() + k);
+            idx = bidx;
+            solved = true;
+          }
+        }
+      }
       std::vector<double> lam, Q;
-      if (sym_eig(Gs, m, lam, Q) && lam[m - 1] > 0.0 && std::isfinite(lam[m - 1])) {
+      if (!solved && sym_eig(Gs, m, lam, Q) && lam[m - 1] > 0.0 && std::isfinite(lam[m - 1])) {
         std::vector<int> keep;
         for (int a = 0; a < m; ++a)
           if (lam[a] > 1e-10 * lam[m - 1]) keep.push_back(a);
@@ -755,10 +819,14 @@ static int gram_general(manisdp_handle* h, const double* A, int lda, int ka, con
   int nchunks = (int)std::min<int64_t>(std::max<int64_t>(1, (32ll << 20) / (int64_t)(nent * 8)), 148);
   nchunks = (int)std::min<int64_t>(nchunks, std::max<int64_t>(1, h->nloc / EIG_TR));
   double *part = nullptr, *dev = nullptr;
-  MSDP_TRY(msdp_scratch(h, 0, (size_t)nchunks * nent * sizeof(double), (void**)&part));
   MSDP_TRY(msdp_scratch(h, 1, nent * sizeof(double), (void**)&dev));
   cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) {
+  if (ka >= 64 && kb >= 64) {
+    // wide factors (BQP-60: p up to ~420): the Gram matrix is a K = n_local GEMM for the FP64 tensor pipe (split-K over
+    // the rows, slices added in order) instead of 32 x 32 FMA tiles -- 9 ms -> well under 1 ms at p = 400
+    MSDP_TRY(msdp_gemm_tn(h, A, lda, ka, B, ldb, kb, h->nloc, dev));
+  } else if (e == cudaSuccess) {
+    MSDP_TRY(msdp_scratch(h, 0, (size_t)nchunks * nent * sizeof(double), (void**)&part));
     dim3 grid(ti, tj, nchunks);
     k_gram_general<<<grid, MSDP_THREADS, 0, h->stream>>>(A, lda, ka, B, ldb, kb, h->nloc, part);
     k_sum_chunks<<<std::max(1, (int)((nent + 255) / 256)), 256, 0, h->stream>>>(part, dev, (int64_t)nent, nchunks);
@@ -795,7 +863,12 @@ static int install_combination(manisdp_handle* h, const std::vector<double>& Cm,
   if (e == cudaSuccess) e = cudaMemcpyAsync(dC, Cm.data(), Cm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess && dD)
     e = cudaMemcpyAsync(dD, Dm.data(), Dm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && ka >= 64) {
+    // wide factors: Y*Cm (+ V*Dm) through the FP64 tensor pipe; the padding columns of tmp stay zero (memset above)
+    MSDP_TRY(msdp_gemm_rows_small(h, h->Ybuf[h->pt], (int)h->ld, ka, dC, pnew, pnew, h->nloc, tmp, (int)ldn, 1.0, 0.0));
+    if (dD) MSDP_TRY(msdp_gemm_rows_small(h, V, ldv, kb, dD, pnew, pnew, h->nloc, tmp, (int)ldn, 1.0, 1.0));
+    e = cudaStreamSynchronize(h->stream);
+  } else if (e == cudaSuccess) {
     const int64_t total = h->nloc * ldn;
     k_rows_times_small<<<std::max(1, (int)std::min<int64_t>(h->num_sms * 8, (total + 255) / 256)), 256, 0, h->stream>>>(
         h->Ybuf[h->pt], (int)h->ld, ka, dC, dD ? V : nullptr, ldv, kb, dD, tmp, (int)ldn, pnew, h->nloc);

@@ -199,3 +199,17 @@ int msdp_gemm_nt(manisdp_handle* h, const double* P, int ldp, const double* Q, i
   GemmArgs g{P, Q, M, nullptr, ldp, 1, 1, ldq, n, n, n, w, 0, alpha, 0.0, pred, pred_sense};
   return launch(h, g);
 }
+
+// G(ka x kb, row stride kb) = P(nrows x ka, ld = ldp)' * Q(nrows x kb, ld = ldq)   -- tall-skinny Gram matrices (rank step)
+int msdp_gemm_tn(manisdp_handle* h, const double* P, int ldp, int ka, const double* Q, int ldq, int kb, int64_t nrows,
+                 double* G) {
+  GemmArgs g{P, Q, G, nullptr, 1, ldp, ldq, 1, kb, ka, kb, (int)nrows, 0, 1.0, 0.0, nullptr, 0};
+  return launch(h, g);
+}
+
+// out(nrows x w, ld = ldo) = alpha * P(nrows x k, ld = ldp) * Cm(k x w, row stride ldc) + beta * out
+int msdp_gemm_rows_small(manisdp_handle* h, const double* P, int ldp, int k, const double* Cm, int ldc, int w,
+                         int64_t nrows, double* out, int ldo, double alpha, double beta) {
+  GemmArgs g{P, Cm, out, nullptr, ldp, 1, ldc, 1, ldo, (int)nrows, w, k, 0, alpha, beta, nullptr, 0};
+  return launch(h, g);
+}

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r2_pytest_full3.log 2>&1; tail -6 gpurun_out/r2_pytest_full3.log
-timeout 900 python bench.py > gpurun_out/r2_bench_n1_b.json 2> gpurun_out/r2_bench_n1_b.err; tail -c 3000 gpurun_out/r2_bench_n1_b.json; tail -3 gpurun_out/r2_bench_n1_b.err
+for s in 0 1 2; do timeout 600 python tools/qs60_gpu.py 60 "{\"delta\": 6, \"seed\": $s}" 2>&1 | tail -1 | cut -c1-330; done

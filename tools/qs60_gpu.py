@@ -18,4 +18,4 @@ t0 = time.perf_counter()
 X, obj, data = ManiSDP(At, np.asarray(b.todense()).ravel() if hasattr(b, "todense") else b, c, K, o)
 print(json.dumps(dict(config="qs60", coe_seed=seed, options=extra, obj=obj, eta=max(data["gap"], data["pinf"], data["dinf"]),
                       iters=data["iters"], hv=data["hv_count"], status=data["status"], seconds=time.perf_counter() - t0,
-                      tr_seconds=data["tr_seconds"], gen_seconds=tg, p_max=max(data["fac_size"]))), flush=True)
+                      tr_seconds=data["tr_seconds"], gen_seconds=tg, phase_seconds=data.get("phase_seconds"), eig_iters=data.get("eig_iters_total"), p_max=max(data["fac_size"]))), flush=True)
