@@ -177,16 +177,39 @@ __global__ void __launch_bounds__(MSDP_THREADS)
   __shared__ double sm[32];
   if (skip_if_stopped && st->stop != 0) return;
   double q[1] = {0.0};
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
-    const int e0 = kptr[k], e1 = kptr[k + 1];
-    double acc = 0.0;
-    for (int e = e0; e < e1; ++e) acc = fma(__ldg(ka + e), __ldg(M + klin[e]), acc);
-    if (mode == 1) {
-      acc = acc - b[k] - y[k] * inv_sigma;
-      q[0] += acc * acc;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // a multiple of 32: the lanes of a warp walk 32 neighbouring constraints
+  const int lane = threadIdx.x & 31;
+  for (int64_t kb = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; kb < m; kb += stride) {
+    const int64_t k = kb + lane;
+    int e0 = 0, e1 = 0;
+    if (k < m) {
+      e0 = kptr[k];
+      e1 = kptr[k + 1];
     }
-    out[k] = acc;
+    // short constraints: one lane each.  LONG ones (a SOS constraint collects every position of S that represents its
+    // monomial: 1831 entries for the constant term of BQP-60, ~60 for a quadratic one) are walked by the whole warp, lane
+    // partial sums joined by the fixed butterfly -- the kernel used to take as long as its longest constraint (335 us).
+    const bool is_long = (e1 - e0) > 32;
+    double acc = 0.0;
+    if (!is_long)
+      for (int e = e0; e < e1; ++e) acc = fma(__ldg(ka + e), __ldg(M + klin[e]), acc);
+    unsigned longmask = __ballot_sync(0xffffffffu, is_long);
+    while (longmask) {
+      const int src = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      const int s0 = __shfl_sync(0xffffffffu, e0, src), s1 = __shfl_sync(0xffffffffu, e1, src);
+      double part = 0.0;
+      for (int e = s0 + lane; e < s1; e += 32) part = fma(__ldg(ka + e), __ldg(M + klin[e]), part);
+      part = warp_sum(part);
+      if (lane == src) acc = part;
+    }
+    if (k < m) {
+      if (mode == 1) {
+        acc = acc - b[k] - y[k] * inv_sigma;
+        q[0] += acc * acc;
+      }
+      out[k] = acc;
+    }
   }
   if (mode == 1) {
     double tot[1];

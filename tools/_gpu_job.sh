@@ -1,2 +1,5 @@
 mkdir -p gpurun_out
-for s in 0 1 2; do timeout 600 python tools/qs60_gpu.py 60 "{\"delta\": 6, \"seed\": $s}" 2>&1 | tail -1 | cut -c1-330; done
+python tools/dual_hv_bench.py 60 64 20
+python tools/mb_hv_bench.py 20 20 100 20
+timeout 900 python -m pytest tests/test_gpu_affine.py tests/test_gpu_dual.py tests/test_gpu_multiblock.py -m gpu -q -x 2>&1 | tail -3
+timeout 300 python tools/run_configs.py bqpdual60 bqp60 2>&1 | cut -c1-260 | tail -2
