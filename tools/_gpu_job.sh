@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
-python tools/dual_hv_bench.py 60 64 20
-python tools/mb_hv_bench.py 20 20 100 20
-timeout 900 python -m pytest tests/test_gpu_affine.py tests/test_gpu_dual.py tests/test_gpu_multiblock.py -m gpu -q -x 2>&1 | tail -3
-timeout 300 python tools/run_configs.py bqpdual60 bqp60 2>&1 | cut -c1-260 | tail -2
+timeout 900 python -m pytest tests/test_gpu_affine.py tests/test_gpu_maxcut.py tests/test_gpu_edges.py tests/test_gpu_dual.py -m gpu -q -x 2>&1 | tail -3
+for c in 0 16; do
+echo "== CHEB $c"
+MANISDP_EIG_CHEB=$c MANISDP_EIG_DEBUG=1 timeout 600 python tools/qs60_gpu.py 60 '{"delta": 6, "seed": 2}' 2>&1 | grep -v "manisdp rank" | tail -2 | cut -c1-420
+MANISDP_EIG_CHEB=$c MANISDP_EIG_DEBUG=1 timeout 300 python tools/run_configs.py theta112 bqp60 2>&1 | grep -v "manisdp rank" | cut -c1-250 | tail -4
+done
