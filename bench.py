@@ -594,14 +594,26 @@ def time_to_kkt_bqp60_dual():
     return out
 
 
+_MB20 = {}
+
+
+def _mb_instance():
+    """the sparse-BQP example of example/example_bqp_sparse.m (built once per process: the Python generator takes ~16 s)"""
+    if not _MB20:
+        from instances import generators as G
+        t0 = time.perf_counter()
+        At, b, c, K, n, I, coe = G.bqp_sparse_instance(20, 20, 1)
+        _MB20.update(At=At, b=b, c=c, K=K, t_gen=time.perf_counter() - t0)
+    return _MB20
+
+
 def time_to_kkt_multiblock():
     """multi-block driver on the reference's own example at its stated size: example/example_bqp_sparse.m,
     t = 20 cliques of q = 20 variables -> 20 unit-diagonal blocks of order 211, m = 327 315."""
     from instances import generators as G
     from manisdp_matlab_b200 import ManiSDP_multiblock
-    t0 = time.perf_counter()
-    At, b, c, K, n, I, coe = G.bqp_sparse_instance(20, 20, 1)
-    t_gen = time.perf_counter() - t0
+    I = _mb_instance()
+    At, b, c, K, t_gen = I["At"], I["b"], I["c"], I["K"], I["t_gen"]
     t0 = time.perf_counter()
     _, obj, data = ManiSDP_multiblock(At, b, c, K, dict(tol=1e-8, line_search=1, tau1=1, verbose=False))
     dt = time.perf_counter() - t0
@@ -684,6 +696,48 @@ def affine_secondary(args, peak):
             rows.append({"p": p, "ms_per_hv": ms, "flops_per_hv": st.flops_per_hv, "achieved_tflops": tf,
                          "frac_of_dgemm_peak": tf / dgemm, "algorithmic_GBps": st.bytes_per_hv / (ms * 1e-3) / 1e9,
                          "s_mode": int(st.s_mode), "a_mode": int(st.a_mode)})
+    # dual driver: the same instance in SOS form through the ManiDSDP_unitdiag closures (dual.cu)
+    try:
+        d = np.load(os.path.join(ROOT, "tests", "golden", "bqp_60_1.npz"))
+        A, bb, dAAt, mb = G.bqpsos(d["Q"], d["e"], 60)
+        with Handle("dual_unitdiag", mb, At=A.T.tocsc(), b=bb / np.abs(bb).max(), c=np.zeros(mb * mb), dAAt=dAAt) as h:
+            h.set_sigma(0.01)
+            drows = []
+            for p in (16, 64):
+                h.rand_Y(p, 1)
+                h.cost()
+                h.slot_set(_lib.SLOT_U, h.project(np.random.default_rng(1).standard_normal((mb, p))))
+                h.hess_bench(3)
+                ms = h.hess_bench(20)
+                st = h.stats()
+                drows.append({"p": p, "ms_per_hv": ms, "flops_per_hv": st.flops_per_hv,
+                              "achieved_tflops": st.flops_per_hv / (ms * 1e-3) / 1e12})
+        out["bqp60_dual_path"] = {"n": int(mb), "m": int(A.shape[0]), "kernels": "K4 x3 + long-constraint gather / scatter "
+                                  "over the SOS pattern + p x p Gram terms (dual.cu)", "rows": drows}
+    except Exception as e:
+        out["bqp60_dual_path"] = {"error": repr(e)}
+    # multi-block driver: K2 + K3 on the sparse-BQP example, dense blocks = long rows (affine.cu)
+    try:
+        I2 = _mb_instance()
+        At2, b2, c2, K2 = I2["At"], I2["b"], I2["c"], I2["K"]
+        ns = K2["s"]
+        with Handle("multiblock", int(sum(ns)), At=At2, b=b2, c=c2, block_sizes=ns, nob=K2["nob"]) as h:
+            h.set_dual(np.zeros(At2.shape[1]), 0.5)
+            mrows = []
+            for p in (16, 100):
+                h.mb_rand_Y([min(p, v) for v in ns], 1)
+                h.cost()
+                h.slot_set(_lib.SLOT_U, h.project(np.random.default_rng(1).standard_normal((h.n, h.p))))
+                h.hess_bench(3)
+                ms = h.hess_bench(20)
+                mrows.append({"p": p, "ms_per_hv": ms, "operand_gather_bytes": float(At2.nnz) * 2 * 8 * h.stats().ld,
+                              "gather_GBps": float(At2.nnz) * 2 * 8 * h.stats().ld / (ms * 1e-3) / 1e9})
+        out["sparse_bqp_multiblock_path"] = {"blocks": len(ns), "block_order": int(ns[0]), "m": int(At2.shape[1]),
+                                             "nnzA": int(At2.nnz), "kernels": "K2 sddmm + K3 row-list (CTA per row for "
+                                             "ld >= 64) over the block-diagonal pattern", "rows": mrows,
+                                             "note": "operands (N x ld) are L1/L2-resident: gather_GBps is cache traffic"}
+    except Exception as e:
+        out["sparse_bqp_multiblock_path"] = {"error": repr(e)}
     out["bqp60_dense_path"] = {"n": n, "m": int(I["At"].shape[1]), "kernels": "K4 FP64 DMMA GEMM (gemm_f64.cu) x3 + A / At "
                                "gathers over the dense pattern (affine.cu)", "rows": rows}
     return out

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmanisdp_b200.so")
-SOURCES = ["api.cu", "tcg.cu", "spmm.cu", "closures.cu", "rtr.cu", "eig.cu", "affine.cu", "gemm_f64.cu", "dist.cu", "colshard.cu", "group.cu", "multiblock.cu", "dual.cu"]
+SOURCES = ["api.cu", "tcg.cu", "spmm.cu", "closures.cu", "rtr.cu", "eig.cu", "affine.cu", "gemm_f64.cu", "dist.cu", "colshard.cu", "group.cu", "multiblock.cu", "dual.cu", "jacobi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=default", "-Xcompiler", "-fopenmp-simd", "-DMSDP_BUILD"]

@@ -217,9 +217,14 @@ struct manisdp_handle {
   int* mb_rowblk = nullptr;              // N: block of each row (device)
   int* mb_roff_dev = nullptr;            // t + 1: row offsets (device)
   int* mb_pw = nullptr;                  // 4t ints: current widths, then work vectors of mb_update (device)
+  int mb_eig_device = 0;                 // 1: batched Jacobi on the device for eig(S{i}) (MANISDP_MB_EIG=device at create)
   int mb_have_eigs = 0;                  // mb_evals / mb_evecs belong to the current point
+  // device: S{i} of the last mb_kkt, overwritten by their eigenvectors (block i at mb_off2[i], row-major n_i x n_i, column k =
+  // k-th vector); Jacobi scratch; eigenvalues
+  double *mb_S = nullptr, *mb_V = nullptr, *mb_w = nullptr;
+  int64_t* mb_off2_dev = nullptr;        // t + 1: offsets of the blocks in mb_S
+  int *mb_n_dev = nullptr, *mb_sweeps = nullptr;  // t: block orders, Jacobi sweeps used
   std::vector<double> mb_evals;          // eigenvalues of every S{i} of the last mb_kkt, stacked by block (ascending)
-  std::vector<double> mb_evecs;          // eigenvectors, block i at mb_off2[i], row-major n_i x n_i (column k = k-th vector)
   DualData dual;
   int rank_strict = 0;                   // rank estimate counts e > theta*e1 (ManiDSDP_unitdiag.m:91) instead of >=
   std::string err;
@@ -230,6 +235,9 @@ int msdp_mb_setup(manisdp_handle* h, const manisdp_problem* pb);
 void msdp_mb_free(manisdp_handle* h);
 double msdp_mb_typicaldist(const manisdp_handle* h);
 double msdp_mb_dim(const manisdp_handle* h);
+// jacobi.cu: batched symmetric eigen-decomposition, one CTA per matrix (eigenvalues ascending in w, eigenvectors in A)
+int msdp_jacobi_batched(manisdp_handle* h, double* A, double* V, double* w, const int64_t* off_dev, const int* woff_dev,
+                        const int* n_dev, int* sweeps_dev, int count, int max_n);
 
 // ---- tracing: one NVTX range per phase of the hot path (visible in Nsight Systems / ncu --nvtx; no cost when no
 // tool is attached: NVTX v3 is header-only and resolves its injection library lazily) -----------------------------

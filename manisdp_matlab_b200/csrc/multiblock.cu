@@ -58,6 +58,34 @@ __global__ void __launch_bounds__(MSDP_THREADS)
   }
 }
 
+// S{i} blocks out of the stacked product AV = S * I(:, c0 : c0 + kc): Sblk[off2[b] + a * n_b + c0 + c] = AV[roff[b] + a, c]
+__global__ void __launch_bounds__(MSDP_THREADS)
+    k_mb_pack_blocks(const double* __restrict__ AV, int kc, int c0, const int* __restrict__ rowblk,
+                     const int* __restrict__ roff, const int64_t* __restrict__ off2, const int* __restrict__ nblk,
+                     double* __restrict__ Sblk, int64_t nrows) {
+  const int64_t total = nrows * kc, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / kc;
+    const int c = (int)(i - r * kc);
+    const int b = rowblk[r], nb = nblk[b];
+    if (c0 + c < nb) Sblk[off2[b] + (int64_t)((int)r - roff[b]) * nb + c0 + c] = AV[i];
+  }
+}
+// S{i} <- (S{i} + S{i}')/2, one CTA per block (the operator is symmetric up to the summation order of its rows)
+__global__ void __launch_bounds__(MSDP_THREADS)
+    k_mb_symmetrize(double* __restrict__ Sblk, const int64_t* __restrict__ off2, const int* __restrict__ nblk) {
+  const int b = blockIdx.x, nb = nblk[b];
+  double* __restrict__ S = Sblk + off2[b];
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+    const int i = e / nb, j = e - i * nb;
+    if (i < j) {
+      const double v = 0.5 * (S[(size_t)i * nb + j] + S[(size_t)j * nb + i]);
+      S[(size_t)i * nb + j] = v;
+      S[(size_t)j * nb + i] = v;
+    }
+  }
+}
+
 // Gram matrices of all blocks, one CTA per block: G[blk][a][b] = sum_{rows of blk} Y[row, a] * Y[row, b]  (a, b < ld)
 // (replaces svd(Y{i}), ManiSDP_multiblock.m:117: the singular values are the roots of the eigenvalues of Y_i' Y_i)
 __global__ void __launch_bounds__(MSDP_THREADS)
@@ -82,8 +110,9 @@ __global__ void __launch_bounds__(MSDP_THREADS)
 __global__ void __launch_bounds__(MSDP_THREADS)
     k_mb_recombine(const double* __restrict__ Y, int ldo, const double* __restrict__ R, const int* __restrict__ rowblk,
                    const int* __restrict__ pold, const int* __restrict__ rcut, const int* __restrict__ nne,
-                   const double* __restrict__ V, int kld, double a, double* __restrict__ out, double* __restrict__ U,
-                   int ldn, int64_t nrows) {
+                   const double* __restrict__ evecs, const int64_t* __restrict__ off2, const int* __restrict__ roff,
+                   const int* __restrict__ nblk, double a, double* __restrict__ out, double* __restrict__ U, int ldn,
+                   int64_t nrows) {
   const int64_t total = nrows * ldn, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t r = i / ldn;
@@ -96,7 +125,7 @@ __global__ void __launch_bounds__(MSDP_THREADS)
       const int po = pold[blk];
       for (int q = 0; q < po; ++q) v = fma(Y[(size_t)r * ldo + q], Rb[(size_t)q * ldn + c], v);
     } else if (c < rc + ne) {
-      u = V[(size_t)r * kld + (c - rc)];
+      u = evecs[off2[blk] + (int64_t)((int)r - roff[blk]) * nblk[blk] + (c - rc)];  // vS{i}(row, c - r_i)
       v = a * u;
     }
     out[i] = v;
@@ -143,6 +172,19 @@ int msdp_mb_setup(manisdp_handle* h, const manisdp_problem* pb) {
   CUDA_TRY(h, cudaMalloc((void**)&h->mb_roff_dev, roff.size() * sizeof(int)));
   CUDA_TRY(h, cudaMemcpy(h->mb_roff_dev, roff.data(), roff.size() * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMalloc((void**)&h->mb_pw, (size_t)4 * t * sizeof(int)));  // widths + three work vectors of mb_update
+  {  // stacked S{i} blocks (become the eigenvectors), Jacobi scratch, eigenvalues, their tables
+    std::vector<int> nd(h->mb_n.begin(), h->mb_n.end());
+    const size_t tot = (size_t)h->mb_off2[t];
+    CUDA_TRY(h, cudaMalloc((void**)&h->mb_S, tot * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->mb_V, tot * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->mb_w, (size_t)h->n * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->mb_off2_dev, ((size_t)t + 1) * sizeof(int64_t)));
+    CUDA_TRY(h, cudaMemcpy(h->mb_off2_dev, h->mb_off2.data(), ((size_t)t + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc((void**)&h->mb_n_dev, (size_t)t * sizeof(int)));
+    CUDA_TRY(h, cudaMemcpy(h->mb_n_dev, nd.data(), (size_t)t * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc((void**)&h->mb_sweeps, (size_t)t * sizeof(int)));
+  }
+  h->mb_eig_device = getenv("MANISDP_MB_EIG") && !strcmp(getenv("MANISDP_MB_EIG"), "device");
   const long long nob_rows = h->mb_nob_rows;
   CUDA_TRY(h, cudaMemcpy(&h->st->nob_rows, &nob_rows, sizeof(long long), cudaMemcpyHostToDevice));
   return MANISDP_OK;
@@ -158,6 +200,12 @@ void msdp_mb_free(manisdp_handle* h) {
   if (h->mb_rowblk) cudaFree(h->mb_rowblk);
   if (h->mb_roff_dev) cudaFree(h->mb_roff_dev);
   if (h->mb_pw) cudaFree(h->mb_pw);
+  void* more[] = {h->mb_S, h->mb_V, h->mb_w, h->mb_off2_dev, h->mb_n_dev, h->mb_sweeps};
+  for (void* q : more)
+    if (q) cudaFree(q);
+  h->mb_S = h->mb_V = h->mb_w = nullptr;
+  h->mb_off2_dev = nullptr;
+  h->mb_n_dev = h->mb_sweeps = nullptr;
   h->mb_rowblk = h->mb_roff_dev = h->mb_pw = nullptr;
 }
 
@@ -270,44 +318,52 @@ extern "C" int manisdp_mb_kkt(manisdp_t* h, int32_t update_dual, manisdp_kkt_inf
   double *V = nullptr, *AV = nullptr;
   MSDP_TRY(msdp_scratch(h, 0, (size_t)h->n * kc * sizeof(double), (void**)&V));
   MSDP_TRY(msdp_scratch(h, 1, (size_t)h->n * kc * sizeof(double), (void**)&AV));
-  std::vector<double> Sb((size_t)h->mb_off2[t], 0.0);  // S{i}, row-major n_i x n_i, at mb_off2[i]
-  std::vector<double> stage((size_t)h->n * kc);
   const auto t_slack0 = std::chrono::steady_clock::now();
   for (int64_t c0 = 0; c0 < nmax; c0 += kc) {
     k_mb_identity<<<mb_grid(h, h->n * kc), MSDP_THREADS, 0, h->stream>>>(V, h->mb_rowblk, h->mb_roff_dev, h->n, kc, (int)c0);
     KERNEL_CHECK(h);
     MSDP_TRY(msdp_affine_apply_S(h, V, AV, kc));
-    CUDA_TRY(h, cudaMemcpyAsync(stage.data(), AV, stage.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < t; ++i) {
-      const int64_t ni = h->mb_n[i];
-      const int64_t cw = std::min<int64_t>(kc, ni - c0);
-      for (int64_t a = 0; a < ni && cw > 0; ++a)
-        memcpy(&Sb[(size_t)h->mb_off2[i] + (size_t)a * ni + (size_t)c0], &stage[(size_t)(h->mb_roff[i] + a) * kc],
-               (size_t)cw * sizeof(double));
-    }
+    k_mb_pack_blocks<<<mb_grid(h, h->n * kc), MSDP_THREADS, 0, h->stream>>>(AV, kc, (int)c0, h->mb_rowblk, h->mb_roff_dev,
+                                                                          h->mb_off2_dev, h->mb_n_dev, h->mb_S, h->n);
+    KERNEL_CHECK(h);
   }
-  g_mb_slack_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_slack0).count();
-  MbSeconds teig(g_mb_eig_s);
-  // eig(S{i}, 'vector') of every block (:90): one dense symmetric eigen-decomposition per block, blocks spread over host
-  // threads (the blocks of a multi-block SDP are small -- 10..200 here -- and independent)
+  k_mb_symmetrize<<<t, MSDP_THREADS, 0, h->stream>>>(h->mb_S, h->mb_off2_dev, h->mb_n_dev);
+  KERNEL_CHECK(h);
+  // eig(S{i}, 'vector') of every block (:90).  Default: Householder + QL per block on host threads (small_eig.h), the
+  // eigenvectors uploaded next to the blocks.  MANISDP_MB_EIG=device (read at create): batched Jacobi, one CTA per block,
+  // the blocks never leave the GPU (jacobi.cu) -- measured SLOWER on one B200 + 16 host threads (20 blocks of order 211:
+  // 148 ms against 17 ms per KKT step; 89 blocks of order <= 55: 2.3 against 1.1 ms): a cyclic Jacobi needs ~10 sweeps of
+  // 3 n^3 flops in ~2000 latency-bound rounds per block, QL ~9 n^3 in cache.  Kept as a tested alternative.
   h->mb_evals.assign((size_t)h->n, 0.0);
-  h->mb_evecs.assign((size_t)h->mb_off2[t], 0.0);
   std::vector<int> ok((size_t)t, 1);
-  auto work = [&](int i) {
-    const int ni = (int)h->mb_n[i];
-    std::vector<double> A((size_t)ni * ni), ev, Z;
-    const double* S = &Sb[(size_t)h->mb_off2[i]];
-    for (int a = 0; a < ni; ++a)
-      for (int b = 0; b < ni; ++b) A[(size_t)a * ni + b] = 0.5 * (S[(size_t)a * ni + b] + S[(size_t)b * ni + a]);
-    if (!sym_eig(A, ni, ev, Z, true, t >= 4 ? 1 : 0)) {  // many blocks: one decomposition per thread, no nested threads
-      ok[(size_t)i] = 0;
-      return;
-    }
-    std::copy(ev.begin(), ev.end(), h->mb_evals.begin() + h->mb_roff[i]);
-    std::copy(Z.begin(), Z.end(), h->mb_evecs.begin() + h->mb_off2[i]);
-  };
-  {
+  if (nmax <= 1024 && h->mb_eig_device) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    g_mb_slack_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_slack0).count();
+    MbSeconds teig(g_mb_eig_s);
+    MSDP_TRY(msdp_jacobi_batched(h, h->mb_S, h->mb_V, h->mb_w, h->mb_off2_dev, h->mb_roff_dev, h->mb_n_dev, h->mb_sweeps, t,
+                                 (int)nmax));
+    std::vector<int> sweeps((size_t)t);
+    CUDA_TRY(h, cudaMemcpyAsync(h->mb_evals.data(), h->mb_w, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(sweeps.data(), h->mb_sweeps, (size_t)t * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < t; ++i) ok[(size_t)i] = sweeps[(size_t)i] > 0 || h->mb_n[i] <= 1;
+  } else {
+    std::vector<double> Sb((size_t)h->mb_off2[t]);  // S{i}, row-major n_i x n_i, at mb_off2[i]
+    CUDA_TRY(h, cudaMemcpyAsync(Sb.data(), h->mb_S, Sb.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    g_mb_slack_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_slack0).count();
+    MbSeconds teig(g_mb_eig_s);
+    std::vector<double> Zall((size_t)h->mb_off2[t], 0.0);
+    auto work = [&](int i) {
+      const int ni = (int)h->mb_n[i];
+      std::vector<double> A(Sb.begin() + h->mb_off2[i], Sb.begin() + h->mb_off2[i + 1]), ev, Z;
+      if (!sym_eig(A, ni, ev, Z, true, t >= 4 ? 1 : 0)) {  // many blocks: one decomposition per thread, no nested threads
+        ok[(size_t)i] = 0;
+        return;
+      }
+      std::copy(ev.begin(), ev.end(), h->mb_evals.begin() + h->mb_roff[i]);
+      std::copy(Z.begin(), Z.end(), Zall.begin() + h->mb_off2[i]);
+    };
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const int T = (int)std::min<unsigned>({hw, 16u, (unsigned)t});
     if (T <= 1) {
@@ -324,6 +380,8 @@ extern "C" int manisdp_mb_kkt(manisdp_t* h, int32_t update_dual, manisdp_kkt_inf
         });
       for (auto& x : th) x.join();
     }
+    // the eigenvectors go where the device path leaves them
+    CUDA_TRY(h, cudaMemcpy(h->mb_S, Zall.data(), Zall.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   for (int i = 0; i < t; ++i)
     if (!ok[(size_t)i]) return msdp_fail(h, MANISDP_E_NUMERIC, "mb_kkt: eigen-decomposition of a block failed");
@@ -360,7 +418,10 @@ extern "C" int manisdp_mb_get_block_eigs(manisdp_t* h, int32_t blk, double* vals
   if (blk < 0 || blk >= (int)h->mb_n.size()) return msdp_fail(h, MANISDP_E_ARG, "mb_get_block_eigs: bad block index");
   const size_t ni = (size_t)h->mb_n[blk];
   if (vals) std::copy_n(h->mb_evals.begin() + h->mb_roff[blk], ni, vals);
-  if (vecs) std::copy_n(h->mb_evecs.begin() + h->mb_off2[blk], ni * ni, vecs);
+  if (vecs) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpy(vecs, h->mb_S + h->mb_off2[blk], ni * ni * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   return MANISDP_OK;
 }
 
@@ -442,11 +503,9 @@ extern "C" int manisdp_mb_update(manisdp_t* h, double theta, int32_t delta, doub
     if (!okb[(size_t)i]) return msdp_fail(h, MANISDP_E_NUMERIC, "mb_update: Gram eigen-decomposition failed");
   int64_t pmax = 1;
   std::vector<int64_t> pn((size_t)t);
-  int nemax = 0;
   for (int i = 0; i < t; ++i) {
     pn[(size_t)i] = rcut[(size_t)i] + nne[(size_t)i];
     pmax = std::max(pmax, pn[(size_t)i]);
-    nemax = std::max(nemax, nne[(size_t)i]);
   }
   if (pmax > MSDP_MAX_LD) return msdp_fail(h, MANISDP_E_ARG, "mb_update: factor width would exceed 512");
   const int ldn = (int)(4 * ((pmax + 3) / 4));
@@ -462,18 +521,10 @@ extern "C" int manisdp_mb_update(manisdp_t* h, double theta, int32_t delta, doub
       for (int q = 0; q < r; ++q) Rb[(size_t)q * ldn + q] = 1.0;
     }
   }
-  // escape directions: the nne_i lowest eigenvectors of S{i}, stacked by rows (N x kld)
-  const int kld = std::max(4, 4 * ((nemax + 3) / 4));
-  std::vector<double> Vh((size_t)h->n * kld, 0.0);
-  for (int i = 0; i < t; ++i) {
-    const int ni = (int)h->mb_n[i];
-    const double* Z = &h->mb_evecs[(size_t)h->mb_off2[i]];
-    for (int a = 0; a < ni; ++a)
-      for (int c = 0; c < nne[(size_t)i]; ++c) Vh[(size_t)(h->mb_roff[i] + a) * kld + c] = Z[(size_t)a * ni + c];
-  }
-  double *Rd = nullptr, *Vd = nullptr, *tmp = nullptr, *Utmp = nullptr;
-  MSDP_TRY(msdp_scratch(h, 1, (R.size() + Vh.size()) * sizeof(double), (void**)&Rd));
-  Vd = Rd + R.size();
+  // escape directions: the nne_i lowest eigenvectors of S{i}, read by the kernel from the stacked blocks mb_kkt left on
+  // the device (h->mb_S)
+  double *Rd = nullptr, *tmp = nullptr, *Utmp = nullptr;
+  MSDP_TRY(msdp_scratch(h, 1, R.size() * sizeof(double), (void**)&Rd));
   const size_t out_elems = (size_t)h->n * ldn;
   MSDP_TRY(msdp_scratch(h, 2, out_elems * (line_search ? 2 : 1) * sizeof(double), (void**)&tmp));
   if (line_search) Utmp = tmp + out_elems;
@@ -484,9 +535,9 @@ extern "C" int manisdp_mb_update(manisdp_t* h, double theta, int32_t delta, doub
   pack.insert(pack.end(), nne.begin(), nne.end());
   CUDA_TRY(h, cudaMemcpyAsync(iw, pack.data(), pack.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(Rd, R.data(), R.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(Vd, Vh.data(), Vh.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   k_mb_recombine<<<mb_grid(h, (int64_t)out_elems), MSDP_THREADS, 0, h->stream>>>(
-      Y, ldo, Rd, h->mb_rowblk, iw, iw + t, iw + 2 * t, Vd, kld, line_search ? 0.0 : alpha, tmp, Utmp, ldn, h->n);
+      Y, ldo, Rd, h->mb_rowblk, iw, iw + t, iw + 2 * t, h->mb_S, h->mb_off2_dev, h->mb_roff_dev, h->mb_n_dev,
+      line_search ? 0.0 : alpha, tmp, Utmp, ldn, h->n);
   KERNEL_CHECK(h);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   // install: the arrays are re-laid out for the new width, the new point goes in as the current one

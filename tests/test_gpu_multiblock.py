@@ -139,8 +139,11 @@ def test_multiblock_tr_iterates_match_oracle(case, use_graph):
 
 
 @pytest.mark.parametrize("case", CASES[:3])
-def test_multiblock_kkt_matches_dense_formulas(case):
-    """ManiSDP_multiblock.m:66-97 against a dense per-block NumPy evaluation (eig of every S{i})"""
+@pytest.mark.parametrize("eig", ["host", "device"])
+def test_multiblock_kkt_matches_dense_formulas(case, eig, monkeypatch):
+    """ManiSDP_multiblock.m:66-97 against a dense per-block NumPy evaluation (eig of every S{i}); both block eigensolvers:
+    Householder + QL on host threads (default) and the batched device Jacobi (MANISDP_MB_EIG=device, csrc/jacobi.cu)"""
+    monkeypatch.setenv("MANISDP_MB_EIG", eig)
     At, b, c, K = _instance(case)
     ns, nob = K["s"], K["nob"]
     rng = np.random.default_rng(3)
@@ -301,12 +304,14 @@ def test_multiblock_equals_single_block_general_on_the_embedding():
 
 # ---- the reference's own multi-block example family: sparse BQP moment relaxations (example/example_bqp_sparse.m) -------
 @pytest.mark.parametrize("t,q,seed", [(3, 4, 1), (3, 5, 2), (4, 4, 3)])
-def test_sparse_bqp_relaxation_is_tight_on_small_instances(t, q, seed):
+def test_sparse_bqp_relaxation_is_tight_on_small_instances(t, q, seed, monkeypatch):
     """oracle-free pin: bqpmom_sparse + ManiSDP_multiblock (all blocks unit-diagonal, options of
     example_bqp_sparse.m:25-29) reach the exhaustive minimum of the clique-sparse BQP over {-1,+1}^n"""
     from instances import generators as G
     from manisdp_matlab_b200 import ManiSDP_multiblock
     At, b, c, K, n, I, coe = G.bqp_sparse_instance(t, q, seed)
+    if seed == 3:  # one of the three instances goes through the device block eigensolver
+        monkeypatch.setenv("MANISDP_MB_EIG", "device")
     X, obj, data = ManiSDP_multiblock(At, b, c, K, dict(tol=1e-8, line_search=1, tau1=1, verbose=False))
     assert data["status"] == 0 and max(data["gap"], data["pinf"], data["dinf"]) < 1e-8
     assert abs(obj - G.bqp_sparse_bruteforce(n, I, coe)) <= 1e-6 * max(1.0, abs(obj))

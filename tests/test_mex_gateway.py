@@ -238,3 +238,44 @@ def test_gateway_drives_a_multiblock_handle():
     mex.call(0, "destroy", None, handle=hd)
     mex.lib.stub_free(hd)
     mex.lib.stub_run_at_exit()
+
+
+@pytest.mark.gpu
+def test_gateway_drives_a_dual_handle():
+    """GPU: a MANISDP_DUAL_UNITDIAG handle through mexFunction (create with At = A(:,K.f+1:end)', dAAt, B, cf as
+    matlab/ManiDSDP_unitdiag.m passes them) gives the numbers of the ctypes binding: tr_solve, the ADMM step, y, x, w."""
+    import scipy.sparse as sp
+    from instances import generators as G
+    from manisdp_matlab_b200 import Handle
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bqp_10_1.npz"))
+    A, b, dAAt, mb = G.bqpsos(d["Q"], d["e"], 10)
+    b = b / np.abs(b).max()
+    m = A.shape[0]
+    B = sp.csc_matrix((np.ones(1), (np.zeros(1, dtype=int), np.zeros(1, dtype=int))), shape=(m, 1))
+    cf, cp = np.array([1.0]), np.zeros(mb * mb)
+    rng = np.random.default_rng(6)
+    Y0 = rng.standard_normal((mb, 5))
+    Y0 /= np.linalg.norm(Y0, axis=1, keepdims=True)
+    with Handle("dual_unitdiag", mb, At=A.T.tocsc(), b=b, c=cp, dAAt=dAAt, B=B, cf=cf) as h:
+        h.set_sigma(1e-3)
+        h.set_Y(Y0)
+        info = h.tr_solve(maxiter=4, maxinner=20, tolgradnorm=1e-8, use_graph=1)
+        k = h.kkt(8, 1e-9, 1)
+        y_ref, _ = h.get_dual()
+        x_ref, w_ref = h.dual_state()
+    mex = Mex()
+    (hd,) = mex.call(1, "create", 5.0, float(mb), A.T.tocsc(), b.reshape(-1, 1), cp.reshape(-1, 1), dAAt.reshape(-1, 1), B,
+                     cf.reshape(-1, 1))
+    mex.call(0, "set_sigma", None, 1e-3, handle=hd)
+    mex.call(0, "set_Y", None, Y0.T, 0.0, handle=hd)
+    (s,) = mex.call(1, "tr_solve", None, dict(maxiter=4, maxinner=20, tolgradnorm=1e-8, use_graph=1), handle=hd)
+    assert mex.field(s, "cost") == info.cost and mex.field(s, "hv_count") == info.hv_count
+    (kk,) = mex.call(1, "kkt", None, 8.0, 1e-9, 1.0, handle=hd)
+    assert mex.field(kk, "obj") == k.obj and mex.field(kk, "pinf") == k.pinf and mex.field(kk, "gap") == k.gap
+    (yy,) = mex.call(1, "get_dual", None, handle=hd)
+    assert np.array_equal(mex.mat(yy).ravel(), y_ref)
+    xx, ww = mex.call(2, "dual_state", None, 1.0, handle=hd)
+    assert np.array_equal(mex.mat(xx).ravel(), x_ref) and np.array_equal(mex.mat(ww).ravel(), w_ref)
+    mex.call(0, "destroy", None, handle=hd)
+    mex.lib.stub_free(hd)
+    mex.lib.stub_run_at_exit()

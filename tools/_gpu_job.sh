@@ -1,7 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_affine.py tests/test_gpu_maxcut.py tests/test_gpu_edges.py tests/test_gpu_dual.py -m gpu -q -x 2>&1 | tail -3
-for c in 0 16; do
-echo "== CHEB $c"
-MANISDP_EIG_CHEB=$c MANISDP_EIG_DEBUG=1 timeout 600 python tools/qs60_gpu.py 60 '{"delta": 6, "seed": 2}' 2>&1 | grep -v "manisdp rank" | tail -2 | cut -c1-420
-MANISDP_EIG_CHEB=$c MANISDP_EIG_DEBUG=1 timeout 300 python tools/run_configs.py theta112 bqp60 2>&1 | grep -v "manisdp rank" | cut -c1-250 | tail -4
-done
+timeout 900 python -m pytest tests/test_gpu_multiblock.py tests/test_mex_gateway.py -m gpu -q -x 2>&1 | tail -5
