@@ -3,8 +3,9 @@
 // One kernel covers the shapes of the dense closures (ManiSDP_unitdiag.m:160-169, ManiSDP.m:157-164):
 //     NN   out(n x w)  = alpha * S(n x n) * V(n x w) + beta * out        (2*eS*U, 4*sigma*AyU*Y, S*V of the eigen step)
 //     NT   M(n x n)    = P(n x w) * Q(n x w)'                            (Y'*U of the reference, row layout)
-// through runtime strides.  Block tile 64x64x16, 8 warps (4 x 2), warp tile 16x32 = 2x4 DMMA tiles, operands staged
-// through a double-buffered shared-memory ring.
+// through runtime strides.  Block tile 64 x BN x 16 with BN = 64 / 32 / 16 chosen from the output width (the LOBPCG block
+// of the eigen step has 12 columns: a 64-wide tile would spend 81 % of its DMMA work on padding), 8 warps (4 x 2), warp
+// tile 16 x BN/2 = 2 x NT DMMA tiles, operands staged through a double-buffered shared-memory ring.
 //
 // SPLIT-K: the NN products are tall-skinny (n = 1831, w = 8..400 on BQP-60): 29 x 5 output tiles at most, each with a
 // 115-step K loop, i.e. the launch is latency bound at < 1 CTA per SM (measured 1.0 ms per Hessian product independent
@@ -15,7 +16,6 @@
 #include "gemm.h"
 
 #define BM 64
-#define BN 64
 #define BK 16
 #define PAD 4
 
@@ -44,6 +44,7 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src, bool o
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
 }
 
+template <int BN>
 __device__ __forceinline__ void load_tiles(const GemmArgs& g, double (*As)[BK + PAD], double (*Bs)[BN + PAD], int m0,
                                            int n0, int k0, int kend, bool a_kfast, bool b_nfast, int tid) {
   for (int i = tid; i < BM * BK; i += 256) {
@@ -75,39 +76,41 @@ __device__ __forceinline__ void load_tiles(const GemmArgs& g, double (*As)[BK + 
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+template <int NT>  // n8 DMMA tiles per warp: block tile width BN = 16 * NT
 __global__ void __launch_bounds__(256) k_gemm_f64(const GemmArgs g) {
   if (g.pred && ((*g.pred == 0) != (g.pred_sense != 0))) return;
+  constexpr int BN = 16 * NT;
   __shared__ double As[2][BM][BK + PAD];
   __shared__ double Bs[2][BK][BN + PAD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
-  double acc[2][4][2];
+  double acc[2][NT][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const bool a_kfast = (g.sak == 1);
   const bool b_nfast = (g.sbn == 1);
   int buf = 0;
-  if (kbeg < kend) load_tiles(g, As[0], Bs[0], m0, n0, kbeg, kend, a_kfast, b_nfast, tid);
+  if (kbeg < kend) load_tiles<BN>(g, As[0], Bs[0], m0, n0, kbeg, kend, a_kfast, b_nfast, tid);
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
     // prefetch the next K tile into the other buffer while this one feeds the tensor pipe
-    if (k0 + BK < kend) load_tiles(g, As[buf ^ 1], Bs[buf ^ 1], m0, n0, k0 + BK, kend, a_kfast, b_nfast, tid);
+    if (k0 + BK < kend) load_tiles<BN>(g, As[buf ^ 1], Bs[buf ^ 1], m0, n0, k0 + BK, kend, a_kfast, b_nfast, tid);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      double a[2], b[4];
+      double a[2], b[NT];
 #pragma unroll
       for (int i = 0; i < 2; ++i) a[i] = As[buf][wm * 16 + i * 8 + (lane >> 2)][kk + (lane & 3)];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][kk + (lane & 3)][wn * 32 + j * 8 + (lane >> 2)];
+      for (int j = 0; j < NT; ++j) b[j] = Bs[buf][kk + (lane & 3)][wn * (8 * NT) + j * 8 + (lane >> 2)];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -117,9 +120,9 @@ __global__ void __launch_bounds__(256) k_gemm_f64(const GemmArgs g) {
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
       const int m = m0 + wm * 16 + i * 8 + (lane >> 2);
-      const int n = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
+      const int n = n0 + wn * (8 * NT) + j * 8 + 2 * (lane & 3);
       if (m < g.M) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(256) k_gemm_reduce(const GemmArgs g, int slice
 }
 
 static int launch(manisdp_handle* h, GemmArgs g) {
+  const int BN = g.N <= 16 ? 16 : (g.N <= 32 ? 32 : 64);
   const int tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
   const int ksteps = (g.K + BK - 1) / BK;
   int slices = 1;
@@ -175,7 +179,12 @@ static int launch(manisdp_handle* h, GemmArgs g) {
     g.ws = h->gemm_ws;
   }
   dim3 grid(tn, tm, slices);
-  k_gemm_f64<<<grid, 256, 0, h->stream>>>(g);
+  if (BN == 16)
+    k_gemm_f64<1><<<grid, 256, 0, h->stream>>>(g);
+  else if (BN == 32)
+    k_gemm_f64<2><<<grid, 256, 0, h->stream>>>(g);
+  else
+    k_gemm_f64<4><<<grid, 256, 0, h->stream>>>(g);
   KERNEL_CHECK(h);
   if (slices > 1) {
     const int64_t total = (int64_t)g.M * g.N;
