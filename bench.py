@@ -77,6 +77,12 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.index = index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        """nvidia-smi is started before the warm-up (its start-up takes longer than a short timed region); only the
+        samples that arrive between mark_begin() and stop() are reported"""
+        self.t_begin = time.perf_counter()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -84,7 +90,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -92,17 +98,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+            self.rows.append((time.perf_counter(), [t.strip() for t in line.split(",")]))
 
     def stop(self):
+        self.t_end = time.perf_counter()
         if self.proc:
+            time.sleep(0.05)  # let the sample that covers the end of the region arrive
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0 = self.t_begin if self.t_begin is not None else -1.0
+        rows = [r for (t, r) in self.rows if t0 <= t <= self.t_end + 0.05]
+        if not rows and self.rows:  # region shorter than one sampling period: the sample closest to it
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + self.t_end)))[1]]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -297,14 +309,15 @@ def run_ours(args, rank, world):
         return (hv_, *tt.tolist())
 
     # ---- device-resident metric -------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     # the bounded CPU sample replays the first timed steps from exactly this point
     Y_timed_start = h.get_Y() if (world == 1 and not args.no_cpu) else None
     l0 = h.stats().launches_total
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     hv, dev_s, wall_s = timed(h, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = h.stats().launches_total - l0
