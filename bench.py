@@ -200,7 +200,7 @@ def run_reference(args, rank):
                              "blas_threads": blas_threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "hv": hv}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -476,7 +476,7 @@ def run_ours(args, rank, world):
         line.update(parity)
     if alt:
         line["alt_layout"] = alt
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def torus_secondary(args, peak):
@@ -756,7 +756,19 @@ def affine_secondary(args, peak):
     return out
 
 
+_JSON_OUT = None
+
+
+def _emit(line):
+    """the ONE JSON line of the contract goes to the process's original stdout; everything else that lands on fd 1
+    (NCCL's version banner at N > 1, solver logs of the kkt entries) was redirected to stderr in main()"""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -781,6 +793,9 @@ def main():
     ap.add_argument("--no-alt", action="store_true", help="N > 1: skip the measurement of the other layout")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
     args = ap.parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.cpu_inner is None:
         args.cpu_inner = args.inner
     if args.ref_inner is None:
