@@ -17,7 +17,7 @@
 #include <stdlib.h>
 #include <chrono>
 // coarse accounting of the eigen step (MANISDP_EIG_DEBUG=1 prints it at destroy): device wait vs host Rayleigh-Ritz
-static double g_eig_wait_s = 0.0, g_eig_host_s = 0.0;
+static double g_eig_wait_s = 0.0, g_eig_host_s = 0.0, g_eig_rr_s = 0.0;  // g_eig_rr_s: Rayleigh-Ritz arithmetic inside g_eig_host_s
 static long g_eig_iters_total = 0;
 // rank step (MANISDP_EIG_DEBUG): Gram kernel + copy, host eigenvalues, host eigenvectors, installing the cut factor
 static double g_rank_gram_s = 0.0, g_rank_vals_s = 0.0, g_rank_vecs_s = 0.0, g_rank_install_s = 0.0;
@@ -493,63 +493,75 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
           Gs[(size_t)a * m + b] = g * dscale[a] * dscale[b];
           As[(size_t)a * m + b] = sgn * ga * dscale[a] * dscale[b];
         }
-      // Fast path: Cholesky of the unit-diagonal Gram matrix (Gs = L L'), At = L^-1 As L^-T, ONE small eigen-solve.  When a
-      // squared pivot falls below 1e-3 (a W or P column close to the span of the others -- typical near convergence and on
-      // the highly degenerate spectra of theta SDPs, where a looser bound was measured to stall the solve) the canonical orthogonalisation
-      // below takes over.  The fast path halves the host time of an iteration (two 36 x 36 decompositions were ~80 % of it:
+      // Fast path: Cholesky of the unit-diagonal Gram matrix (Gs = L L'), At = L^-1 As L^-T, ONE small eigen-solve instead of
+      // the two of the canonical orthogonalisation (two 36 x 36 decompositions were ~80 % of the host time of an iteration:
       // 52 500 iterations on the q = 60 quartic, 9.8 s of its 22.6 s).
       {
-        std::vector<double> L((size_t)m * m, 0.0);
+        // Cholesky over the basis columns in order X | W | P; a W or P column whose squared pivot is below 1e-3 (less than
+        // 3 % of it is outside the span of the columns before it) is DROPPED -- it gets zero coefficients, exactly what the
+        // canonical orthogonalisation does to a dependent direction -- so that L stays well conditioned (the Ritz values
+        // keep ~13 digits) and one eigen-solve per iteration suffices also on the degenerate spectra of theta SDPs, where
+        // nearly every iteration has such a column.  A small pivot on an X column means the block itself degenerated: the
+        // canonical path below takes over.
+        std::vector<int> kept;
+        std::vector<double> L((size_t)m * m, 0.0);  // row a of L (over the kept columns) at L[a*m ..]
         bool chol_ok = true;
         for (int a = 0; a < m && chol_ok; ++a) {
-          for (int b = 0; b <= a; ++b) {
-            double sum = Gs[(size_t)a * m + b];
-            for (int q = 0; q < b; ++q) sum -= L[(size_t)a * m + q] * L[(size_t)b * m + q];
-            if (a == b) {
-              if (!(sum > 1e-3)) {
-                chol_ok = false;
-                break;
-              }
-              L[(size_t)a * m + a] = sqrt(sum);
-            } else {
-              L[(size_t)a * m + b] = sum / L[(size_t)b * m + b];
-            }
+          const int nk = (int)kept.size();
+          double* La = &L[(size_t)nk * m];  // provisional row: becomes row nk of the compact factor if the column is kept
+          for (int b = 0; b < nk; ++b) {
+            double sum = Gs[(size_t)a * m + kept[(size_t)b]];
+            const double* Lb = &L[(size_t)b * m];
+            for (int q = 0; q < b; ++q) sum -= La[q] * Lb[q];
+            La[b] = sum / Lb[b];
           }
+          double d = Gs[(size_t)a * m + a];
+          for (int q = 0; q < nk; ++q) d -= La[q] * La[q];
+          if (!(d > 1e-3)) {
+            if (a < k) chol_ok = false;  // X column
+            continue;                    // W / P column: dropped
+          }
+          La[nk] = sqrt(d);
+          kept.push_back(a);
         }
-        if (chol_ok) {
-          // T1 = L^-1 As  (forward substitution, column by column), At = T1 L^-T = (L^-1 T1')'
-          std::vector<double> T1((size_t)m * m), At((size_t)m * m);
-          for (int c = 0; c < m; ++c)
-            for (int a = 0; a < m; ++a) {
-              double sum = As[(size_t)a * m + c];
-              for (int q = 0; q < a; ++q) sum -= L[(size_t)a * m + q] * T1[(size_t)q * m + c];
-              T1[(size_t)a * m + c] = sum / L[(size_t)a * m + a];
+        const int mk = (int)kept.size();
+        if (chol_ok && mk >= k) {
+          // T1 = L^-1 As(kept, kept)  (forward substitution, column by column), At = T1 L^-T = (L^-1 T1')'
+          std::vector<double> T1((size_t)mk * mk), At((size_t)mk * mk);
+          for (int c = 0; c < mk; ++c)
+            for (int a = 0; a < mk; ++a) {
+              double sum = As[(size_t)kept[(size_t)a] * m + kept[(size_t)c]];
+              const double* La = &L[(size_t)a * m];
+              for (int q = 0; q < a; ++q) sum -= La[q] * T1[(size_t)q * mk + c];
+              T1[(size_t)a * mk + c] = sum / La[a];
             }
-          for (int r = 0; r < m; ++r)      // row r of T1, solve L x = T1(r, :)'  ->  At(r, :) = x'
-            for (int a = 0; a < m; ++a) {
-              double sum = T1[(size_t)r * m + a];
-              for (int q = 0; q < a; ++q) sum -= L[(size_t)a * m + q] * At[(size_t)r * m + q];
-              At[(size_t)r * m + a] = sum / L[(size_t)a * m + a];
+          for (int r = 0; r < mk; ++r)  // row r of T1: solve L x = T1(r, :)'  ->  At(r, :) = x'
+            for (int a = 0; a < mk; ++a) {
+              double sum = T1[(size_t)r * mk + a];
+              const double* La = &L[(size_t)a * m];
+              for (int q = 0; q < a; ++q) sum -= La[q] * At[(size_t)r * mk + q];
+              At[(size_t)r * mk + a] = sum / La[a];
             }
-          for (int r = 0; r < m; ++r)
-            for (int q = r + 1; q < m; ++q) {
-              const double v = 0.5 * (At[(size_t)r * m + q] + At[(size_t)q * m + r]);
-              At[(size_t)r * m + q] = At[(size_t)q * m + r] = v;
+          for (int r = 0; r < mk; ++r)
+            for (int q = r + 1; q < mk; ++q) {
+              const double v = 0.5 * (At[(size_t)r * mk + q] + At[(size_t)q * mk + r]);
+              At[(size_t)r * mk + q] = At[(size_t)q * mk + r] = v;
             }
           std::vector<double> ev, Zt;
-          bool okeig = sym_eig(At, m, ev, Zt);
+          bool okeig = sym_eig(At, mk, ev, Zt);
           for (int c = 0; okeig && c < k; ++c) okeig = std::isfinite(ev[c]);
           if (okeig) {
-            // C = L^-T Zt(:, 0:k)  (back substitution), then undo the diagonal scaling
+            // C(kept, :) = L^-T Zt(:, 0:k)  (back substitution), dropped columns keep zero coefficients; undo the scaling
             Cfull.assign((size_t)m * k, 0.0);
+            std::vector<double> Ck((size_t)mk * k);
             for (int c = 0; c < k; ++c)
-              for (int a = m - 1; a >= 0; --a) {
-                double sum = Zt[(size_t)a * m + c];
-                for (int q = a + 1; q < m; ++q) sum -= L[(size_t)q * m + a] * Cfull[(size_t)q * k + c];
-                Cfull[(size_t)a * k + c] = sum / L[(size_t)a * m + a];
+              for (int a = mk - 1; a >= 0; --a) {
+                double sum = Zt[(size_t)a * mk + c];
+                for (int q = a + 1; q < mk; ++q) sum -= L[(size_t)q * m + a] * Ck[(size_t)q * k + c];
+                Ck[(size_t)a * k + c] = sum / L[(size_t)a * m + a];
               }
-            for (int a = 0; a < m; ++a)
-              for (int c = 0; c < k; ++c) Cfull[(size_t)a * k + c] *= dscale[a];
+            for (int a = 0; a < mk; ++a)
+              for (int c = 0; c < k; ++c) Cfull[(size_t)kept[(size_t)a] * k + c] = Ck[(size_t)a * k + c] * dscale[kept[(size_t)a]];
             ritz.assign(ev.begin(), ev.begin() + k);
             idx = bidx;
             solved = true;
@@ -602,6 +614,7 @@ static int lobpcg(manisdp_handle* h, EigWork& w, int nwant, int want_largest, do
         }
       }
     }
+    g_eig_rr_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count();
     if (!solved) {
       if (!haveW) return msdp_fail(h, MANISDP_E_NUMERIC, "lobpcg: starting block is rank deficient");
       break;  // basis degenerated: accept the current Ritz pairs
@@ -690,8 +703,8 @@ static std::mutex g_store_mu;
 void msdp_eig_release(manisdp_handle* h) {
   std::lock_guard<std::mutex> lk(g_store_mu);
   if (getenv("MANISDP_EIG_DEBUG") && g_eig_iters_total > 0)
-    fprintf(stderr, "[manisdp eig] iterations %ld, device wait %.3f s, host part (RR + launches) %.3f s\n",
-            g_eig_iters_total, g_eig_wait_s, g_eig_host_s);
+    fprintf(stderr, "[manisdp eig] iterations %ld, device wait %.3f s, host part (RR + launches) %.3f s of which Rayleigh-Ritz "
+                    "arithmetic %.3f s\n", g_eig_iters_total, g_eig_wait_s, g_eig_host_s, g_eig_rr_s);
   if (getenv("MANISDP_EIG_DEBUG") && g_rank_calls > 0)
     fprintf(stderr, "[manisdp rank] %ld decompositions: gram+copy %.3f s, eigenvalues (incl. gram) %.3f s, eigenvectors %.3f s, "
                     "install %.3f s\n", g_rank_calls, g_rank_gram_s, g_rank_vals_s, g_rank_vecs_s, g_rank_install_s);

@@ -185,8 +185,11 @@ MSDP_EIG_CLONES inline bool sym_eig(const std::vector<double>& A, int n, std::ve
   const double eps = 2.220446049250313e-16;
   // the rotations of the QL sweeps are recorded and applied to the accumulated transformation afterwards, rows split over
   // a few host threads (every row of V sees the same sequence of rotations, independently of the other rows)
+  // small matrices (the <= 48 x 48 Rayleigh-Ritz problems of LOBPCG, thousands per solve): the whole V sits in L1, so each
+  // rotation is applied on the spot (two unit-stride columns) instead of being recorded and replayed in row blocks
+  const bool direct = n <= 64;
   std::vector<EigRotation> rot;
-  if (want_vectors) rot.reserve((size_t)n * (size_t)n);
+  if (want_vectors && !direct) rot.reserve((size_t)n * (size_t)n);
   for (int l = 0; l < n; ++l) {
     tst1 = std::max(tst1, fabs(w[l]) + fabs(e[l]));
     int m = l;
@@ -225,7 +228,20 @@ MSDP_EIG_CLONES inline bool sym_eig(const std::vector<double>& A, int n, std::ve
           c = p / r;
           p = c * w[i] - s * g;
           w[i + 1] = h + s * (c * g + s * w[i]);
-          if (want_vectors) rot.push_back(EigRotation{i, c, s});
+          if (want_vectors) {
+            if (direct) {
+              double* __restrict__ ci = &v(0, i);
+              double* __restrict__ cj = &v(0, i + 1);
+              MSDP_SIMD
+              for (int k = 0; k < n; ++k) {
+                const double hk = cj[k];
+                cj[k] = s * ci[k] + c * hk;
+                ci[k] = c * ci[k] - s * hk;
+              }
+            } else {
+              rot.push_back(EigRotation{i, c, s});
+            }
+          }
         }
         p = -s * s2 * c3 * el1 * e[l] / dl1;
         e[l] = s * p;

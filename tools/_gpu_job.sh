@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q -x > gpurun_out/r2_pytest_sharded.log 2>&1; tail -4 gpurun_out/r2_pytest_sharded.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; tail -c 1500 gpurun_out/r2_bench_n2.json; tail -3 gpurun_out/r2_bench_n2.err
+timeout 900 python -m pytest tests/test_gpu_affine.py tests/test_gpu_maxcut.py tests/test_gpu_edges.py tests/test_gpu_dual.py -m gpu -q -x 2>&1 | tail -3
+MANISDP_EIG_DEBUG=1 timeout 600 python tools/qs60_gpu.py 60 '{"delta": 6, "seed": 2}' 2>&1 | grep -v "manisdp rank" | tail -2 | cut -c1-300
+MANISDP_EIG_DEBUG=1 timeout 300 python tools/run_configs.py theta112 theta102 bqp60 bqpdual60 2>&1 | grep -v "manisdp rank" | cut -c1-230 | tail -8
