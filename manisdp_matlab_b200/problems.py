@@ -91,40 +91,3 @@ def read_sdpa(path):
     c = -sp.csc_matrix((vals[obj], (rows[obj], np.zeros(obj.sum(), dtype=np.int64))), shape=(n * n, 1))
     At = sp.csc_matrix((vals[~obj], (rows[~obj], cols[~obj] - 1)), shape=(n * n, m))
     return At, b, c, {"s": n}
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# multi-block SDPs through the single-block engine
-# ---------------------------------------------------------------------------------------------------------------------
-def embed_blocks(At, c, K, b=None, nob=0):
-    """SeDuMi data of a multi-block SDP (K['s'] = [n_1, ..., n_t], rows of At / c index the concatenation of the
-    column-major vec(X_i)) -> data of ONE block of order N = sum n_i whose cost and constraints only touch the diagonal
-    blocks.  The two SDPs have the same optimum and the same dual slack (block diag(S_i)): off-diagonal blocks of X are
-    neither priced nor constrained, and X >= 0 iff it can be completed from PSD diagonal blocks.  The first `nob`
-    blocks are unit-diagonal in the reference driver (src/primal/ManiSDP_multiblock.m:1-5); here those diagonal
-    constraints are appended to (At, b) explicitly.  Returns (At_big, b_big, c_big, N, offsets)."""
-    ns = np.atleast_1d(np.asarray(K["s"] if isinstance(K, dict) else K)).astype(np.int64)
-    off = np.concatenate([[0], np.cumsum(ns)])            # row/column offset of block i in the big matrix
-    voff = np.concatenate([[0], np.cumsum(ns * ns)])      # offset of vec(X_i) in the concatenated vector
-    N = int(off[-1])
-
-    def remap(r):
-        r = np.asarray(r, dtype=np.int64)
-        blk = np.searchsorted(voff, r, side="right") - 1
-        loc = r - voff[blk]
-        i = loc % ns[blk]
-        j = loc // ns[blk]
-        return (off[blk] + j) * N + (off[blk] + i)
-
-    At = sp.coo_matrix(At)
-    At_big = sp.csc_matrix((At.data, (remap(At.row), At.col)), shape=(N * N, At.shape[1]))
-    cc = sp.coo_matrix(c.reshape(-1, 1) if not sp.issparse(c) else sp.csc_matrix(c).reshape(-1, 1))
-    c_big = sp.csc_matrix((cc.data, (remap(cc.row), np.zeros(cc.nnz, dtype=np.int64))), shape=(N * N, 1))
-    b_big = None if b is None else (np.asarray(b.todense()).ravel() if sp.issparse(b) else np.asarray(b, float).ravel())
-    if nob > 0:
-        d = np.arange(off[nob], dtype=np.int64)
-        D = sp.csc_matrix((np.ones(len(d)), (d * N + d, np.arange(len(d)))), shape=(N * N, len(d)))
-        At_big = sp.hstack([At_big, D], format="csc")
-        if b_big is not None:
-            b_big = np.concatenate([b_big, np.ones(len(d))])
-    return At_big, b_big, c_big, N, off

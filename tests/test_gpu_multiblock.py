@@ -340,3 +340,29 @@ def test_sparse_bqp_example_at_its_stated_size():
             break
     assert data["status"] == 0 and max(data["gap"], data["pinf"], data["dinf"]) < 1e-8, tried
     assert abs(obj - gold["obj"]) <= 1e-6 * abs(gold["obj"]), tried
+
+
+def test_multiblock_index_split_matches_the_authors_embedding():
+    """data/SDP_demo_1.mat (89 blocks of order 55 / 10 / 10 ...): the (row, column) pairs the engine derives from the
+    stacked-vec row indices of At equal the block-diagonal embedding, which tests/test_host_generators.py pins against
+    the authors' own single-block form of the same SDP (sedumi.At_full) -- a golden vector of the reference for the
+    index handling of the multi-block path (BASELINE north_star: bit-exact A(YY') indices)."""
+    import os
+    import scipy.sparse as sp
+    from instances import generators as G
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdp_demo_1.npz"))
+    At = sp.csc_matrix((d["At_data"], d["At_indices"], d["At_indptr"]), shape=tuple(d["At_shape"]))
+    At.sort_indices()
+    c = np.zeros(At.shape[0])
+    c[d["c_idx"]] = d["c_val"]
+    ns = [int(v) for v in d["ns"]]
+    N = int(sum(ns))
+    # entry e of At (CSC order) -> its row in the embedded N*N x m matrix: embed a copy whose values are the entry numbers
+    emb = sp.coo_matrix(G.embed_blocks(sp.csc_matrix((np.arange(1, At.nnz + 1, dtype=np.float64), At.indices, At.indptr),
+                                                    shape=At.shape), c, {"s": ns}, d["b"])[0])
+    order = np.argsort(emb.data)
+    rows = emb.row[order]
+    with _handle(At, d["b"], c, {"s": ns, "nob": 0}) as h:
+        i, j = h.index_split()
+    assert len(i) == At.nnz
+    assert np.array_equal(i, rows % N) and np.array_equal(j, rows // N)

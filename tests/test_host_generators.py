@@ -17,11 +17,13 @@ def test_bqpmom_sizes_match_reference_log():
 
 
 def test_embed_blocks_against_reference_single_block_form():
-    """multi-block -> single-block index embedding (groundwork for SURVEY 8f rank 3).  data/SDP_demo_1.mat carries the
-    authors' own single-block version of the same SDP (sedumi.At_full / c_full): every embedded column must appear
-    there, in order, and c must match exactly."""
+    """multi-block -> single-block index embedding (the map the engine applies at create for MANISDP_MULTIBLOCK handles,
+    csrc/affine.cu `split`; its read-back is compared with this embedding on the GPU in
+    tests/test_gpu_multiblock.py::test_multiblock_index_split_matches_the_authors_embedding).  data/SDP_demo_1.mat
+    carries the authors' own single-block version of the same SDP (sedumi.At_full / c_full): every embedded column must
+    appear there, in order, and c must match exactly."""
     import scipy.sparse as sp
-    from manisdp_matlab_b200 import problems as P
+    from instances import generators as P
     d = np.load(os.path.join(GOLDEN, "sdp_demo_1.npz"))
     At = sp.csc_matrix((d["At_data"], d["At_indices"], d["At_indptr"]), shape=tuple(d["At_shape"]))
     c = sp.csc_matrix((d["c_val"], (d["c_idx"], np.zeros(len(d["c_idx"]), dtype=int))), shape=(At.shape[0], 1))
