@@ -203,6 +203,7 @@ def test_dual_bqp60_reaches_the_baseline_optimum():
     gold = json.load(open(os.path.join(GOLDEN, "oracle_outputs_large.json")))
     A2, b, c, K, dAAt, maxb, _ = _sos(60)
     assert (K["s"], A2.shape[0]) == (gold["bqp_60_1_dual"]["n"], gold["bqp_60_1_dual"]["m"])
+    assert (K["s"], A2.shape[0] - 1) == (1831, 523685)  # data/bqp_result.txt:27 (the authors' dual run at d = 60: 20.5 s)
     _, obj, data = ManiDSDP_unitdiag(A2, b, c, K, dict(dAAt=dAAt, tol=1e-8, line_search=1, verbose=False))
     assert data["status"] == 0 and max(data["gap"], data["pinf"], data["dinf"]) < 1e-8
     assert abs(obj * maxb - gold["bqp_60_1_dual"]["obj"]) <= 1e-6 * abs(gold["bqp_60_1_dual"]["obj"])

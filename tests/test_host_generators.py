@@ -54,3 +54,17 @@ def test_embed_blocks_against_reference_single_block_form():
             where.setdefault(key(Af, k), k)
         pos = [where.get(key(Ab, k), -1) for k in range(Ab.shape[1])]
         assert min(pos) >= 0 and all(a < b for a, b in zip(pos, pos[1:]))
+
+
+def test_bqpsos_sizes_match_the_reference_dual_table():
+    """data/bqp_result.txt:20-27 (the authors' ManiDSDP log): d = 10 / 20 / 30 -> n = 56 / 211 / 466 and m = 385 / 6195 /
+    31930 equality constraints, i.e. one per non-constant multilinear monomial of degree <= 4 -- the restated bqpsos
+    returns that many rows plus the row of the constant term; diag(A*A') counts the positions of every monomial."""
+    from instances import generators as G
+    rng = np.random.default_rng(0)
+    for d, n, m in [(10, 56, 385), (20, 211, 6195), (30, 466, 31930)]:
+        Q = rng.standard_normal((d, d))
+        A, b, dAAt, mb = G.bqpsos(Q + Q.T, rng.standard_normal(d), d)
+        assert (mb, A.shape[0] - 1, A.shape[1]) == (n, m, n * n)
+        assert A.nnz == n * n and dAAt.sum() == n * n and dAAt[0] == n  # a partition of the positions
+        assert np.array_equal(np.asarray(A.sum(axis=1)).ravel(), dAAt)
