@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_baseline_configs.py tests/test_gpu_multiblock.py -m gpu -q -x 2>&1 | tail -15
+timeout 1500 python tools/run_configs.py bqpdual130 2>&1 | grep "^{" | cut -c1-700 | tee gpurun_out/r2_bqpdual130.jsonl

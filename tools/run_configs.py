@@ -81,7 +81,13 @@ def run(name, cpu):
         import scipy.sparse as sp_
         from instances import generators as gi
         q = int(name[len("bqpdual"):])
-        d = np.load(os.path.join(GOLDEN, f"bqp_{q}_1.npz"))
+        fn = os.path.join(GOLDEN, f"bqp_{q}_1.npz")
+        if os.path.exists(fn):
+            d = np.load(fn)
+        else:  # beyond the reference's data files (d <= 60): example_bqp_dual.m:2-5 with NumPy's generator, seed = q
+            rq = np.random.default_rng(q)
+            Qs = rq.standard_normal((q, q))
+            d = {"Q": (Qs + Qs.T) / 2, "e": rq.standard_normal(q)}
         A, bb, dAAt, mb = gi.bqpsos(d["Q"], d["e"], q)
         v = np.zeros((A.shape[0], 1))
         v[0] = 1.0
