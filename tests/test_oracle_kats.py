@@ -124,3 +124,27 @@ def test_multiblock_oracle_pinned_by_the_single_block_driver():
     for Xi in X:
         assert np.allclose(np.diag(Xi), 1.0, atol=1e-12)
     assert all(np.linalg.eigvalsh(S)[0] > -1e-6 for S in d3["S"])  # dual feasibility of the slack blocks
+
+
+def test_dual_oracle_pinned_by_bruteforce_and_strong_duality():
+    """ManiDSDP_unitdiag's restatement (src/dual/ManiDSDP_unitdiag.m) on the SOS form of the reference's BQP data files:
+    d = 10 reaches the exhaustive minimum over {-1,+1}^10 (the relaxation is tight there), d = 20 the optimum of the
+    primal moment relaxation already pinned above (strong duality), with the options of example/dual/example_bqp_dual.m."""
+    import scipy.sparse as sp
+    from instances import generators as G
+    from oracle.manisdp_ref import ManiDSDP_unitdiag
+    gold = json.load(open(os.path.join(GOLDEN, "oracle_outputs.json")))
+    for q, target in [(10, None), (20, gold["bqp_20_1_opt"]["obj"])]:
+        d = np.load(os.path.join(GOLDEN, f"bqp_{q}_1.npz"))
+        A, b, dAAt, mb = G.bqpsos(d["Q"], d["e"], q)
+        v = np.zeros((A.shape[0], 1))
+        v[0] = 1.0
+        A2 = sp.hstack([sp.csr_matrix(v), A]).tocsr()
+        c = np.concatenate([[1.0], np.zeros(mb * mb)])
+        maxb = float(np.abs(b).max())
+        X, obj, data = ManiDSDP_unitdiag(A2, b / maxb, c, {"f": 1, "s": mb}, dict(dAAt=dAAt, tol=1e-8, line_search=1))
+        assert data["status"] == 0 and max(data["gap"], data["pinf"], data["dinf"]) < 1e-8
+        if target is None:
+            target = G.bqp_bruteforce(d["Q"], d["e"])
+        assert abs(obj * maxb - target) <= 1e-6 * abs(target), (q, obj * maxb, target)
+        assert np.allclose(np.diag(data["S"]), 1.0, atol=1e-12) and np.linalg.eigvalsh(X)[0] > -1e-6
