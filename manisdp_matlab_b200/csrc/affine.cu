@@ -1027,10 +1027,10 @@ static int apply_S_sparse(manisdp_handle* h, const double* V1, const double* vec
   a.skip_if_stopped = skip_if_stopped;
   // long rows (on average >= 64 entries) and full-warp row groups: one CTA per row
   static const int wide_on = getenv("MANISDP_K3_WIDE") ? atoi(getenv("MANISDP_K3_WIDE")) : 1;  // A/B switch
-  if (wide_on && h->As.nnz >= 64 * h->n && ld >= 64 && h->n <= (int64_t)h->num_sms * 64) {
+  if (wide_on && h->As.nnz >= 64 * h->n && ld >= 64 && ld <= MSDP_MAX_LD && h->n <= (int64_t)h->num_sms * 64) {
     const int nb = (int)std::min<int64_t>(h->n, (int64_t)h->num_sms * 8);
     DISPATCH_GEOM(row_geom(ld), {
-      if (GS == 32) k_rowlist_apply_wide<VPL><<<nb, MSDP_THREADS, 0, h->stream>>>(a, h->st);
+      if (GS == 32 && VPL <= 8) k_rowlist_apply_wide<(VPL <= 8 ? VPL : 8)><<<nb, MSDP_THREADS, 0, h->stream>>>(a, h->st);
     });
     KERNEL_CHECK(h);
     return MANISDP_OK;

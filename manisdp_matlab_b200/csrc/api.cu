@@ -94,11 +94,14 @@ int msdp_scratch(manisdp_handle* h, int slot, size_t bytes, void** out) {
 int msdp_resize(manisdp_handle* h, int64_t p) {
   if (p < 1) return msdp_fail(h, MANISDP_E_ARG, "p must be >= 1");
   const int64_t ld = 4 * ((p + 3) / 4);
-  if (ld > MSDP_MAX_LD) return msdp_fail(h, MANISDP_E_ARG, "factor width p > 512 is not supported");
+  const int64_t max_ld = (h->kind == MANISDP_ONLYUNITDIAG || h->kind == MANISDP_MULTIBLOCK) ? MSDP_MAX_LD : MSDP_MAX_LD_AFFINE;
+  if (ld > max_ld)
+    return msdp_fail(h, MANISDP_E_ARG, max_ld == MSDP_MAX_LD ? "factor width p > 512 is not supported for this kind"
+                                                            : "factor width p > 1024 is not supported");
   const size_t need = (size_t)rows_alloc(h) * (size_t)ld;
   if (need > h->cap_elems) {
     // grow with headroom: the outer loop appends up to delta columns per iteration
-    const int64_t ld_cap = std::min<int64_t>(MSDP_MAX_LD, 4 * ((ld + ld / 2 + 16 + 3) / 4));
+    const int64_t ld_cap = std::min<int64_t>(max_ld, 4 * ((ld + ld / 2 + 16 + 3) / 4));
     const size_t cap = (size_t)rows_alloc(h) * (size_t)ld_cap;
     double** arrs[] = {&h->Ybuf[0], &h->Ybuf[1], &h->Gbuf[0], &h->Gbuf[1], &h->eta[0], &h->eta[1],
                        &h->r,       &h->d,       &h->Hd,      &h->Uslot,   &h->Hslot};

@@ -271,7 +271,9 @@ int msdp_fail(manisdp_handle* h, int code, const std::string& msg);
 
 // ---- row-group geometry -----------------------------------------------------------------------------------------
 // A row of ld doubles (ld % 4 == 0) is handled by GS lanes, each holding VPL double2 vectors: vector index
-// v = lane + GS*t.  GS in {2,4,8,16,32}, VPL in {1,2,4,8}  =>  ld <= 512.
+// v = lane + GS*t.  GS in {2,4,8,16,32}, VPL in {1,2,4,8,16}  =>  ld <= 1024 for the affine / dual kinds (the VPL = 16
+// instances spill registers and exist for completeness: BQP d >= 120 needs p > 512); the MaxCut kernels of spmm.cu and
+// the multi-block tables stop at ld = 512.
 struct RowGeom {
   int gs, vpl;
 };
@@ -282,7 +284,8 @@ inline RowGeom row_geom(int64_t ld) {
   while (g.gs * g.vpl < nvec) g.vpl *= 2;
   return g;
 }
-#define MSDP_MAX_LD 512
+#define MSDP_MAX_LD 512          // ONLYUNITDIAG (spmm.cu kernels), multi-block
+#define MSDP_MAX_LD_AFFINE 1024  // UNITDIAG / UNITTRACE / GENERAL / DUAL_UNITDIAG
 
 #define DISPATCH_GEOM(geom, ...)                                            \
   do {                                                                      \
@@ -297,7 +300,8 @@ inline RowGeom row_geom(int64_t ld) {
       }                                                                     \
     } else if (_g.vpl == 2) { constexpr int GS = 32, VPL = 2; __VA_ARGS__; } \
     else if (_g.vpl == 4) { constexpr int GS = 32, VPL = 4; __VA_ARGS__; }  \
-    else { constexpr int GS = 32, VPL = 8; __VA_ARGS__; }                   \
+    else if (_g.vpl == 8) { constexpr int GS = 32, VPL = 8; __VA_ARGS__; }  \
+    else { constexpr int GS = 32, VPL = 16; __VA_ARGS__; }                  \
   } while (0)
 
 // grid for a row-group kernel over nrows rows

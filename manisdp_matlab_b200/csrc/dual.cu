@@ -249,7 +249,7 @@ static int dual_gram_buffers(manisdp_handle* h) {
   const int ld = (int)h->ld;
   if (d.gram_ld >= ld && d.gram[0]) return MANISDP_OK;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  const int cap = std::min<int>(MSDP_MAX_LD, ld + ld / 2 + 16);
+  const int cap = std::min<int>(MSDP_MAX_LD_AFFINE, ld + ld / 2 + 16);
   double** bufs[] = {&d.gram[0], &d.gram[1], &d.gramS, &d.gramW};
   for (double** b : bufs) {
     if (*b) cudaFree(*b);

@@ -265,3 +265,37 @@ def test_theta_full_solve():
                                                              line_search=1))
     assert max(data["gap"], data["pinf"], data["dinf"]) < 1e-6
     assert abs(obj - (-128.0 / 3.0)) <= 1e-4 * 42.67
+
+
+@pytest.mark.parametrize("kind", ["unitdiag", "unittrace", "general"])
+def test_affine_closures_at_widths_beyond_512(kind):
+    """factor widths 512 < p <= 1024 (row groups with 16 vectors per lane): cost / grad / hess and the manifold operations
+    against the oracle on BQP-20 (n = 211) at p = 600 -- the reference has no width limit; BQP d >= 120 needs p > 512"""
+    from manisdp_matlab_b200 import Handle
+    from oracle.manisdp_ref import AffineProblem
+    At, b, c, n = _bqp(20)
+    m, p = At.shape[1], 600
+    Y, rng = _point(kind, n, p, 5)
+    U = rng.standard_normal((n, p))
+    y = 0.3 * rng.standard_normal(m)
+    sigma = 0.7
+    ora = AffineProblem(kind, At.tocsc(), b, _dense_c(c), n, p, y, sigma)
+    f0 = ora.cost(Y)
+    g0 = ora.grad(Y)
+    Ut = ora.M.proj(Y, U)
+    H0 = ora.hess(Y, Ut)
+    R0 = ora.M.retr(Y, 0.1 * Ut)
+    for mode in ("auto", "sparse"):
+        with Handle(kind, n, At=At, b=b, c=c, force_mode=FORCE[mode]) as h:
+            h.set_dual(y, sigma)
+            h.set_Y(Y)
+            f = h.cost()
+            G, gn = h.grad()
+            P = h.project(U)
+            Hd = h.hess(Ut)
+            R = h.retract(0.1 * Ut)
+        assert abs(f - f0) <= 1e-11 * max(1.0, abs(f0))
+        assert _rel(G, g0) < 1e-11 and _rel(P, Ut) < 1e-12 and _rel(Hd, H0) < 1e-10 and _rel(R, R0) < 1e-12
+    with Handle(kind, n, At=At, b=b, c=c) as h:
+        with pytest.raises(Exception, match="1024"):
+            h.set_Y(np.zeros((n, 1030)))

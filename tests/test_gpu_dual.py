@@ -208,3 +208,31 @@ def test_dual_bqp60_reaches_the_baseline_optimum():
     assert data["status"] == 0 and max(data["gap"], data["pinf"], data["dinf"]) < 1e-8
     assert abs(obj * maxb - gold["bqp_60_1_dual"]["obj"]) <= 1e-6 * abs(gold["bqp_60_1_dual"]["obj"])
     assert abs(obj * maxb - gold["bqp_60_1_opt"]["obj"]) <= 1e-6 * abs(gold["bqp_60_1_opt"]["obj"])
+
+
+def test_dual_closures_at_widths_beyond_512():
+    """p = 640 on the SOS form of BQP-20: the dual closures (Gram terms included) beyond the 512-column row geometry"""
+    from oracle.manisdp_ref import DualProblem
+    A2, b, c, K, dAAt, _, _ = _sos(20)
+    n, nf, m = K["s"], K["f"], A2.shape[0]
+    A, B = A2[:, nf:].tocsr(), A2[:, :nf].tocsr()
+    rng = np.random.default_rng(77)
+    x, w = _state(n, m, nf, rng)
+    x = _project_out(A, dAAt, x)
+    sigma, p = 0.21, 640
+    Y = rng.standard_normal((n, p))
+    Y /= np.linalg.norm(Y, axis=1, keepdims=True)
+    ora = DualProblem(A, B, b, c[nf:], c[:nf], n, p, dAAt, x, w, sigma)
+    f0 = ora.cost(Y)
+    g0 = ora.grad(Y)
+    U = ora.M.proj(Y, rng.standard_normal((n, p)))
+    H0 = ora.hess(Y, U)
+    with _handle(A2, b, c, K, dAAt) as h:
+        h.set_sigma(sigma)
+        h.dual_set_state(x, w)
+        h.set_Y(Y)
+        f = h.cost()
+        G, gn = h.grad()
+        Hd = h.hess(U)
+    assert abs(f - f0) <= 1e-11 * max(1.0, abs(f0))
+    assert _rel(G, g0) < 1e-11 and _rel(Hd, H0) < 1e-10
