@@ -22,8 +22,9 @@
  *     Host buffers passed to set/get are either MANISDP_LAYOUT_ROWS (n x p row-major == MATLAB p x n column-major,
  *     the layout of the unit-diagonal drivers, ManiSDP_unitdiag.m:53) or MANISDP_LAYOUT_COLS (n x p column-major,
  *     MATLAB's layout in ManiSDP.m / ManiSDP_unittrace.m).
- *   - Limits of this implementation (the reference has none): factor width p <= 512 (row-group geometry of the fused
- *     kernels; manisdp_set_Y / escape / mb_update fail with MANISDP_E_ARG beyond it), n and m < 2^31, dense S for
+ *   - Limits of this implementation (the reference has none): factor width p <= 1024 on the affine and dual kinds,
+ *     p <= 512 on ONLYUNITDIAG and MULTIBLOCK handles (row-group geometry of the fused kernels; manisdp_set_Y / escape /
+ *     mb_update fail with MANISDP_E_ARG beyond it), n and m < 2^31, dense S for
  *     n <= 40000, options.delta <= 60, block orders <= 1024 for the device block eigensolver.
  *   - A handle is single-caller (not re-entrant); different handles may be used from different threads.
  *   - There is no CPU fallback: every compute entry point fails with MANISDP_E_CUDA when no sm_100 device works.

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_affine.py tests/test_gpu_dual.py -m gpu -q -x -k "beyond_512" 2>&1 | tail -12
+timeout 1700 python tools/run_configs.py bqpdual130 2>&1 | grep "^{" | cut -c1-700 | tee gpurun_out/r2_bqpdual130.jsonl
