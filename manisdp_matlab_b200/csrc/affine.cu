@@ -510,6 +510,108 @@ __global__ void __launch_bounds__(MSDP_THREADS) k_rowlist_apply_wide(RowlistArgs
   }
 }
 
+// The same for NARROW operands (ld < 64, i.e. fewer than 32 vectors per row: the first and the last outer iterations of
+// a multi-block solve, where the factors are thin).  A warp splits into 32 / GS sub-groups of GS lanes; every sub-group
+// takes its own entry of the 32-entry batch, so 32 / GS operand rows are gathered at once and four steps are in flight;
+// the sub-group accumulators are joined by a butterfly over the lane bits above GS, the warps through shared memory.
+template <int GS>
+__global__ void __launch_bounds__(MSDP_THREADS) k_rowlist_apply_wide_narrow(RowlistArgs a, RtrState* st) {
+  __shared__ double2 part[MSDP_THREADS / 32][32];
+  if (a.pred && *a.pred == 0) return;
+  if (a.skip_if_stopped && st->stop != 0) return;
+  constexpr int NW = MSDP_THREADS / 32, NG = 32 / GS;
+  const int lane = threadIdx.x % 32, wid = threadIdx.x / 32, gl = lane % GS, grp = lane / GS;
+  const int nvec = a.ld / 2, ld = a.ld;
+  const bool colok = gl < nvec;
+  for (int64_t row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+    double2 acc = make_double2(0.0, 0.0);
+    if (a.cval && wid == 0 && grp == 0) {
+      for (int e = a.crowptr[row]; e < a.crowptr[row + 1]; ++e) {
+        const double w = a.alphaC * __ldg(a.cval + e);
+        if (colok) {
+          const double2 u = ldg2(a.V1 + (size_t)__ldg(a.ccol + e) * ld + 2 * gl);
+          acc.x = fma(w, u.x, acc.x);
+          acc.y = fma(w, u.y, acc.y);
+        }
+      }
+    }
+    const int e0 = a.rptr[row], e1 = a.rptr[row + 1];
+    for (int eb = e0 + 32 * wid; eb < e1; eb += 32 * NW) {
+      const int e = eb + lane;
+      int j = 0;
+      double w1 = 0.0, w2 = 0.0;  // lanes past the end of the row carry zero weights and a valid row index (0)
+      if (e < e1) {
+        const double av = __ldg(a.ra + e);
+        j = __ldg(a.rj + e);
+        const int k = __ldg(a.rk + e);
+        if (a.vec1) w1 = a.c1 * av * __ldg(a.vec1 + k);
+        if (a.vec2) w2 = a.c2 * av * __ldg(a.vec2 + k);
+      }
+      const int cnt = min(32, e1 - eb);
+      for (int u = 0; u < cnt; u += 4 * NG) {
+        size_t jo[4];
+        double a1[4], a2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int src = (u + q * NG + grp) & 31;  // entries past cnt have zero weights (w1 = w2 = 0 beyond the row)
+          const bool live = (u + q * NG + grp) < 32;
+          jo[q] = (size_t)__shfl_sync(0xffffffffu, j, src) * ld;
+          a1[q] = __shfl_sync(0xffffffffu, w1, src);
+          a2[q] = __shfl_sync(0xffffffffu, w2, src);
+          if (!live) {
+            a1[q] = 0.0;
+            a2[q] = 0.0;
+            jo[q] = 0;
+          }
+        }
+        if (colok) {
+          double2 x1[4], x2[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (a.vec1) x1[q] = ldg2(a.V1 + jo[q] + 2 * gl);
+            if (a.vec2) x2[q] = ldg2(a.V2 + jo[q] + 2 * gl);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (a.vec1) {
+              acc.x = fma(a1[q], x1[q].x, acc.x);
+              acc.y = fma(a1[q], x1[q].y, acc.y);
+            }
+            if (a.vec2) {
+              acc.x = fma(a2[q], x2[q].x, acc.x);
+              acc.y = fma(a2[q], x2[q].y, acc.y);
+            }
+          }
+        }
+      }
+    }
+    // join the sub-groups of the warp (lane bits GS, 2GS, ...), then the warps
+#pragma unroll
+    for (int off = GS; off < 32; off <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+    }
+    if (grp == 0 && colok) part[wid][gl] = acc;
+    __syncthreads();
+    const size_t rb = (size_t)row * ld;
+    for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
+      double2 sres = part[0][c];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) {
+        sres.x += part[w][c].x;
+        sres.y += part[w][c].y;
+      }
+      if (a.beta != 0.0) {
+        const double2 o = ld2(a.out + rb + 2 * c);
+        sres.x = fma(a.beta, o.x, sres.x);
+        sres.y = fma(a.beta, o.y, sres.y);
+      }
+      st2(a.out + rb + 2 * c, sres);
+    }
+    __syncthreads();
+  }
+}
+
 // cost scalars: f = <C,X> + sigma/2 |r|^2  (ManiSDP_unitdiag.m:156)
 __global__ void k_cost_finish(RtrState* st, double sigma, int mode, int w, int dual) {
   // dual handles: tmp[6] = sigma/2 |Z'Z|_F^2 + sigma/2 |Af|^2 + k0 (dual.cu: msdp_dual_cost_extra)
@@ -1027,10 +1129,13 @@ static int apply_S_sparse(manisdp_handle* h, const double* V1, const double* vec
   a.skip_if_stopped = skip_if_stopped;
   // long rows (on average >= 64 entries) and full-warp row groups: one CTA per row
   static const int wide_on = getenv("MANISDP_K3_WIDE") ? atoi(getenv("MANISDP_K3_WIDE")) : 1;  // A/B switch
-  if (wide_on && h->As.nnz >= 64 * h->n && ld >= 64 && ld <= MSDP_MAX_LD && h->n <= (int64_t)h->num_sms * 64) {
+  if (wide_on && h->As.nnz >= 64 * h->n && ld <= MSDP_MAX_LD && h->n <= (int64_t)h->num_sms * 64) {
     const int nb = (int)std::min<int64_t>(h->n, (int64_t)h->num_sms * 8);
     DISPATCH_GEOM(row_geom(ld), {
-      if (GS == 32 && VPL <= 8) k_rowlist_apply_wide<(VPL <= 8 ? VPL : 8)><<<nb, MSDP_THREADS, 0, h->stream>>>(a, h->st);
+      if (GS == 32 && VPL <= 8)
+        k_rowlist_apply_wide<(VPL <= 8 ? VPL : 8)><<<nb, MSDP_THREADS, 0, h->stream>>>(a, h->st);
+      else if (GS < 32)
+        k_rowlist_apply_wide_narrow<(GS < 32 ? GS : 16)><<<nb, MSDP_THREADS, 0, h->stream>>>(a, h->st);
     });
     KERNEL_CHECK(h);
     return MANISDP_OK;

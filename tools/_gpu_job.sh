@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r2_pytest_full5.log 2>&1; tail -5 gpurun_out/r2_pytest_full5.log
-timeout 900 python bench.py > gpurun_out/r2_bench_n1_d.json 2> gpurun_out/r2_bench_n1_d.err; wc -l gpurun_out/r2_bench_n1_d.json; tail -1 gpurun_out/r2_bench_n1_d.err | cut -c1-200
-python -c "import __graft_entry__ as g; g.smoke()"
+timeout 900 python -m pytest tests/test_gpu_multiblock.py -m gpu -q -x 2>&1 | tail -4
+python tools/mb_hv_bench.py 20 20 16 20
+python tools/mb_hv_bench.py 20 20 4 20
+python tools/mb_hv_bench.py 20 20 40 20
+timeout 300 python tools/run_configs.py bqpsparse:20x20 2>&1 | cut -c1-300 | tail -1
