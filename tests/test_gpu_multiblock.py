@@ -366,3 +366,51 @@ def test_multiblock_index_split_matches_the_authors_embedding():
         i, j = h.index_split()
     assert len(i) == At.nnz
     assert np.array_equal(i, rows % N) and np.array_equal(j, rows // N)
+
+
+@pytest.mark.parametrize("p", [[64, 62], [66, 66], [3, 5], [20, 17], [1, 1], [40, 33]])
+def test_multiblock_closures_on_long_rows(p):
+    """dense blocks give the row-list kernel LONG rows (here ~130 entries per row): the one-CTA-per-row forms of K3
+    (affine.cu: k_rowlist_apply_wide for >= 32 vectors per row, k_rowlist_apply_wide_narrow below that) against the
+    oracle's dense cell-array closures, and the KKT step (S * identity through the same kernels) against NumPy"""
+    from instances import generators as G
+    from oracle.manisdp_ref import MultiblockProblem
+    from oracle.manopt_rtr import Cells
+    At, b, c, K, n, I, coe = G.bqp_sparse_instance(2, 10, 5)
+    ns, nob = K["s"], K["nob"]
+    assert At.nnz >= 64 * sum(ns)
+    rng = np.random.default_rng(23)
+    Y = _point(ns, nob, p, rng)
+    y = 0.2 * rng.standard_normal(At.shape[1])
+    sigma = 1.3
+    ora = MultiblockProblem(At.tocsc(), b, c, ns, p, nob, y, sigma)
+    Yc = Cells(Y)
+    f0 = ora.cost(Yc)
+    g0 = ora.grad(Yc)
+    U = ora.M.proj(Yc, Cells([rng.standard_normal(B.shape) for B in Y]))
+    H0 = ora.hess(Yc, U)
+    # dual slack blocks after the dual update, dense on the host
+    X = [B @ B.T for B in Y]
+    x = np.concatenate([Xi.reshape(-1, order="F") for Xi in X])
+    y1 = y - sigma * (At.T @ x - b)
+    cy = c - At @ y1
+    off2 = np.concatenate([[0], np.cumsum([v * v for v in ns])])
+    with _handle(At, b, c, K) as h:
+        h.set_dual(y, sigma)
+        h.mb_set_Y(Y)
+        f = h.cost()
+        Gd, gn = h.grad()
+        Hd = h.hess(h.mb_join(U.b))
+        Gs, Hs = h.mb_split(Gd), h.mb_split(Hd)
+        k, dinfs, nneg = h.mb_kkt(update_dual=1)
+        for i, nb in enumerate(ns):
+            Si = cy[off2[i]:off2[i + 1]].reshape(nb, nb, order="F")
+            Si = Si - np.diag(np.sum(X[i] * Si, axis=0))
+            vals, vecs = h.mb_block_eigs(i)
+            ev = np.linalg.eigvalsh(Si)
+            assert np.allclose(vals, ev, rtol=0, atol=1e-11 * max(1.0, np.abs(ev).max()))
+            assert np.linalg.norm(Si @ vecs - vecs * vals) < 1e-10 * max(1.0, np.abs(ev).max())
+    assert abs(f - f0) <= 1e-12 * max(1.0, abs(f0))
+    for i in range(len(ns)):
+        assert _rel(Gs[i], g0[i]) < 1e-12
+        assert _rel(Hs[i], H0[i]) < 1e-11

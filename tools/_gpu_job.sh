@@ -1,6 +1,5 @@
+# scratch job script for `gpurun -- 'bash tools/_gpu_job.sh'` (edited per experiment); the round's final check was:
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multiblock.py -m gpu -q -x 2>&1 | tail -4
-python tools/mb_hv_bench.py 20 20 16 20
-python tools/mb_hv_bench.py 20 20 4 20
-python tools/mb_hv_bench.py 20 20 40 20
-timeout 300 python tools/run_configs.py bqpsparse:20x20 2>&1 | cut -c1-300 | tail -1
+timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; wc -l gpurun_out/bench_n1.json
+python -c "import __graft_entry__ as g; g.smoke()"
