@@ -61,9 +61,15 @@ def test_no_gpu_means_loud_failure(engine_lib):
 def test_host_small_eigensolver(engine_lib):
     from manisdp_matlab_b200 import _lib
     rng = np.random.default_rng(0)
-    for n in [1, 2, 7, 36, 48, 130]:
-        A = rng.standard_normal((n, n))
-        A = A + A.T
+    for n in [1, 2, 7, 36, 48, 64, 65, 130, -40, -90]:  # negative: a degenerate spectrum (three distinct eigenvalues)
+        if n > 0:
+            A = rng.standard_normal((n, n))
+            A = A + A.T
+        else:
+            n = -n
+            Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+            A = (Q * rng.choice([-1.0, 0.0, 2.5], size=n)) @ Q.T
+            A = 0.5 * (A + A.T)
         w = np.empty(n)
         V = np.empty((n, n))
         assert engine_lib.manisdp_test_sym_eig(_lib._pf(np.ascontiguousarray(A)), n, _lib._pf(w), _lib._pf(V)) == 0
