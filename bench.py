@@ -378,9 +378,11 @@ def run_ours(args, rank, world):
         del Yo
 
     # ---- roofline of the dominant kernel (live CUDA-event timing inside the library) -----------------------------
-    st = h.stats()
     U = np.random.default_rng(1).standard_normal(Y0.shape)
     h.set_Y(Y0p)
+    st = h.stats()  # after the reset to the configured width: the outer-iteration measurement above appended columns, and
+    # the algorithmic bytes of the roofline must be those of the width the kernel is timed at
+    assert int(st.p) == p, (int(st.p), p)
     h.slot_set(_lib.SLOT_U, U)
     h.hess_bench(3)
     ms = h.hess_bench(args.hv_reps)
